@@ -1,0 +1,137 @@
+/* polar_b200.h -- C ABI of the B200 (sm_100a) polar-code hot path.
+ *
+ * Drop-in boundary for jaco267/polar-code-pytorch-sionna.  The reference has no FFI (it is pure
+ * Python); the boundary it exposes is the nn.Module call surface of its encoder / decoders / link
+ * model.  Each entry point below replaces the *body* of one of those Python methods; the Python
+ * mirror under polar-code-pytorch-sionna_b200/{x_run_sn_polar,my_sn} keeps the reference signatures
+ * and calls these through ctypes (x_run_sn_polar/d_kernels.py is the loader).  Reference file:line
+ * cited per function are relative to the reference checkout.
+ *
+ * Conventions
+ *  - Every pointer named d_* is a DEVICE pointer into caller-owned memory (e.g. a torch CUDA
+ *    tensor's data_ptr()); h_* is a HOST pointer.  No torch types cross this boundary.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device entry
+ *    points only enqueue work: they never synchronise and never allocate.
+ *  - Bit packing: bit (i % 32) of 32-bit word (i / 32) holds position i (LSB first); a row of n
+ *    positions occupies POLAR_WORDS(n) = max(1, n/32) words.
+ *  - Logits follow the reference decoder input: ln P(1)/P(0), fp32, row-major [B, n]
+ *    (polar_sc.py:113-122).  Decisions are bit-exact with the reference on the same logits.
+ *  - Return value: POLAR_OK (0) or a negative POLAR_E* code; polar_last_error() gives the text
+ *    (thread local).  The Python mirror turns codes into the reference's exception types.
+ */
+#ifndef POLAR_B200_H_
+#define POLAR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POLAR_OK 0
+#define POLAR_EINVAL (-1)   /* bad n / L / k / B, or null pointer                     */
+#define POLAR_EALIGN (-2)   /* pointer not aligned as documented                      */
+#define POLAR_ENOMEM (-3)   /* workspace too small / shared memory does not fit       */
+#define POLAR_ECUDA (-4)    /* CUDA runtime error (launch failed, no device ...)      */
+
+#define POLAR_MAX_N 8192    /* SC decoder / encoder / front end                       */
+#define POLAR_SCL_MAX_N 4096
+#define POLAR_SCL_MAX_L 32
+#define POLAR_WORDS(n) ((n) < 32 ? 1 : (n) / 32)
+
+const char *polar_last_error(void);
+/* library / device info: writes "polar_b200 <version> sm_100a ..." */
+const char *polar_version(void);
+/* number of kernels this library has launched in the calling process (bench.py: gpu_launches) */
+unsigned long long polar_launch_count(void);
+
+/* ---- SC decoder --------------------------------------------------------------------------
+ * Replaces SC_Dec._decode_batch + _polar_decode_sc_tf + _cn_op_tf/_vn_op_tf + the info_pos gather
+ * (x_run_sn_polar/polar/polar_sc.py:33-133).  fp32 min-sum, f clipped to +-30, g unclipped.
+ *  d_logit        [B, n] fp32, 16-byte aligned rows (n >= 4) -- NOT negated by the caller
+ *  d_frozen_mask  [POLAR_WORDS(n)] bit set = frozen position (polar_sc.py:23-24)
+ *  d_u_packed     [B, POLAR_WORDS(n)] all n decisions, frozen = 0 (msg_uhat[:,0,:]); may be NULL
+ *  d_u_info_f32   [B, k] fp32 0./1. at ascending info_pos (the tensor SC_Dec.forward returns);
+ *                 may be NULL.  d_info_pos [k] int32 (required iff d_u_info_f32 != NULL)
+ *  n power of two, 2 <= n <= POLAR_MAX_N. */
+int polar_sc_decode_f32(const float *d_logit, const uint32_t *d_frozen_mask, int n, int64_t B,
+                        uint32_t *d_u_packed, float *d_u_info_f32, const int32_t *d_info_pos, int k,
+                        void *stream);
+
+/* ---- SCL decoder -------------------------------------------------------------------------
+ * Replaces SCL_Dec._decode_np_batch and everything under it (x_run_sn_polar/polar/polar_scl.py:49-209),
+ * the argmin/gather of forward (:224-228) and, when crc_len > 0, the CRC-aided selection of
+ * my_sn/fec/polar/dec.py:507-527 (+ my_sn/fec/crc.py:119-138).  fp64 LLR tree and path metrics,
+ * pm += log(1+exp(-x)); lazy copy-on-write of the tree through per-stage pointer tables.
+ *  L power of two, 1 <= L <= 32; n power of two, 2 <= n <= POLAR_SCL_MAX_N
+ *  d_best_packed  [B, POLAR_WORDS(n)] decisions of the selected path
+ *  d_u_info_f32   [B, k] fp32 or NULL (as above)
+ *  d_pm_sorted    [B, L] fp64 ascending path metrics (before any CRC penalty) or NULL
+ *  d_list_packed  [B, L, POLAR_WORDS(n)] decisions of all L survivors, pm-ascending, or NULL
+ *  d_crc_rows     [n] uint32: for info position i, the crc_len-bit syndrome contribution of that bit
+ *                 (row of the reference's [k, crc_len] generator matrix, crc.py:54-74, MSB = parity
+ *                 bit 0); 0 for frozen positions.  NULL / crc_len == 0: plain argmin.
+ *  d_workspace    polar_scl_workspace_bytes(n, L, B) bytes, 256-byte aligned. */
+size_t polar_scl_workspace_bytes(int n, int L, int64_t B);
+int polar_scl_decode(const float *d_logit, const uint32_t *d_frozen_mask, int n, int L, int64_t B,
+                     uint32_t *d_best_packed, float *d_u_info_f32, const int32_t *d_info_pos, int k,
+                     double *d_pm_sorted, uint32_t *d_list_packed,
+                     const uint32_t *d_crc_rows, int crc_len,
+                     void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* ---- encoder -----------------------------------------------------------------------------
+ * polar_encode_packed: x = u.G over GF(2) on bit-packed rows (XOR butterfly; the transform of
+ * my_sn/fec/polar/enc.py:85-96 == (c @ G) % 2 of x_run_sn_polar/polar/enc.py:42).
+ * polar_encode_f32: the whole PolarEncoder.forward (x_run enc.py:30-43 / my_sn enc.py:97-113):
+ * scatter u[B,k] (fp32 0/1) to info positions, transform, write c[B,n] fp32 0/1.
+ *  d_info_rank [n] int32: index into u for info positions, -1 for frozen. */
+int polar_encode_packed(const uint32_t *d_u_full_packed, int n, int64_t B, uint32_t *d_c_packed,
+                        void *stream);
+int polar_encode_f32(const float *d_u, const int32_t *d_info_rank, int n, int k, int64_t B,
+                     float *d_c, uint32_t *d_c_packed_or_null, void *stream);
+
+/* ---- BPSK/AWGN LLR front end -----------------------------------------------------------------
+ * Replaces System_AWGN_model.forward up to the decoder call (z_sys_model/awgn_model.py:33-40):
+ * BinarySource -> PolarEncoder -> Mapper (QPSK = BPSK per dimension, amplitude 1/sqrt2) -> AWGN
+ * (variance no/2 per real dimension) -> Demapper (closed form logit = -2.sqrt2.y/no).
+ * Random numbers: counter-based Philox4x32-10 keyed by (seed, codeword index + offset); the
+ * stream is a pure function of (seed, offset, b, i), independent of launch geometry.
+ *  d_u_packed_out [B, POLAR_WORDS(n)] transmitted u (info bits at info positions, frozen 0)
+ *  d_c_packed_out [B, POLAR_WORDS(n)] transmitted codeword, or NULL
+ *  d_logit_out    [B, n] fp32 */
+int polar_awgn_frontend(uint64_t seed, uint64_t offset, float no, const uint32_t *d_frozen_mask,
+                        int n, int64_t B, uint32_t *d_u_packed_out, uint32_t *d_c_packed_out,
+                        float *d_logit_out, void *stream);
+/* Channel + demapper only, for caller-supplied codewords (Mapper/AWGN/Demapper layers,
+ * my_sn/trans/mapping.py:136-149,225-241, my_sn/trans/channel/awgn.py:19-29). */
+int polar_qpsk_awgn_llr(uint64_t seed, uint64_t offset, float no, const float *d_c /*[B,n] 0/1*/,
+                        int n, int64_t B, float *d_logit_out, void *stream);
+
+/* ---- error counting ------------------------------------------------------------------------
+ * count_errors / count_block_errors (my_sn/sim.py:7-18).  d_counters[0] += bit errors,
+ * d_counters[1] += block errors (unsigned 64-bit, caller zeroes them). */
+int polar_count_errors_packed(const uint32_t *d_a, const uint32_t *d_b, const uint32_t *d_mask_or_null,
+                              int n, int64_t B, unsigned long long *d_counters, void *stream);
+int polar_count_errors_f32(const float *d_b, const float *d_b_hat, int k, int64_t B,
+                           unsigned long long *d_counters, void *stream);
+
+/* ---- bit (un)packing helpers used by the Python mirror ---------------------------------------- */
+int polar_pack_bits_f32(const float *d_x /*[B,n] 0/1*/, int n, int64_t B, uint32_t *d_packed, void *stream);
+int polar_unpack_info_f32(const uint32_t *d_packed, const int32_t *d_pos /*[k]*/, int n, int k, int64_t B,
+                          float *d_out /*[B,k]*/, void *stream);
+
+/* ---- host-buffer entry points (end-to-end path: H2D + decode + D2H inside the call) -------------
+ * Same semantics as the device entry points but with HOST buffers; the batch is cut into chunks
+ * that are copied, decoded and copied back on two streams so PCIe transfers overlap the kernels.
+ * h_logit should be page-locked for full overlap (pageable memory works, slower).  Synchronous. */
+int polar_sc_decode_host(const float *h_logit, const uint32_t *h_frozen_mask, int n, int64_t B,
+                         uint32_t *h_u_packed, int device);
+int polar_scl_decode_host(const float *h_logit, const uint32_t *h_frozen_mask, int n, int L, int64_t B,
+                          uint32_t *h_best_packed, double *h_pm_sorted_or_null,
+                          const uint32_t *h_crc_rows_or_null, int crc_len, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLAR_B200_H_ */

@@ -1,0 +1,180 @@
+// polar_enc.cu -- bit-packed XOR-butterfly polar encoder + bit (un)packing helpers (sm_100a).
+//
+// Replaces PolarEncoder.forward: x_run_sn_polar/polar/enc.py:30-43 (scatter + dense (c@G)%2) and
+// my_sn/fec/polar/enc.py:85-113 (gather/xor stages).  c_j = XOR_{i superset j} u_i.
+// One warp per codeword, 32 positions per lane-word; stages below 32 are in-register shifts,
+// stages 32..1023 are __shfl_xor, stages above are register-to-register.  HBM-bound.
+#include "polar_internal.h"
+#include "polar_warp.cuh"
+
+namespace polar {
+
+// ---- packed -> packed ------------------------------------------------------------------------
+// n <= 1024: a warp carries 32/nw codewords (lane = cw_local*nw + word).
+__global__ void __launch_bounds__(256) enc_packed_small_kernel(const uint32_t *__restrict__ u, int m, int nw,
+                                                               int64_t nwords_total, uint32_t *__restrict__ c) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = warp0 * 32; base < nwords_total; base += nwarps * 32) {
+    const int64_t idx = base + lane;
+    uint32_t x = idx < nwords_total ? __ldg(u + idx) : 0u;
+    x = ptransform_rt(x, m);
+    for (int d = 1; d < nw; d <<= 1) {
+      const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, x, d);
+      if (!(lane & d)) x ^= y;
+    }
+    if (idx < nwords_total) c[idx] = x;
+  }
+}
+// n >= 1024: one codeword per warp, R = n/1024 words per lane.
+template <int R>
+__global__ void __launch_bounds__(256) enc_packed_kernel(const uint32_t *__restrict__ u, int m, int64_t B,
+                                                         uint32_t *__restrict__ c) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t b = warp0; b < B; b += nwarps) {
+    uint32_t x[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) x[r] = __ldg(u + b * (R * 32) + r * 32 + lane);
+    warp_polar_transform<R>(x, m, R * 32);
+#pragma unroll
+    for (int r = 0; r < R; ++r) c[b * (R * 32) + r * 32 + lane] = x[r];
+  }
+}
+
+// ---- fp32 API tensor in / out: whole PolarEncoder.forward --------------------------------------
+template <int R>
+__global__ void __launch_bounds__(256) enc_f32_kernel(const float *__restrict__ u, const int32_t *__restrict__ info_rank,
+                                                      int n, int m, int k, int64_t B, float *__restrict__ c,
+                                                      uint32_t *__restrict__ c_packed) {
+  const int lane = threadIdx.x & 31;
+  const int nw = n < 32 ? 1 : n >> 5;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t b = warp0; b < B; b += nwarps) {
+    uint32_t x[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) x[r] = 0u;
+    // scatter: position p takes u[b, rank(p)] (enc.py:33-35); frozen positions stay 0
+    for (int wd = 0; wd < nw; ++wd) {
+      const int p = wd * 32 + lane;
+      int bit = 0;
+      if (p < n) {
+        const int rk = __ldg(info_rank + p);
+        if (rk >= 0) bit = (__ldg(u + b * (int64_t)k + rk) != 0.0f);
+      }
+      const uint32_t w = __ballot_sync(0xFFFFFFFFu, bit);
+      if (lane == (wd & 31)) x[R == 1 ? 0 : (wd >> 5)] = w;
+    }
+    warp_polar_transform<R>(x, m, nw);
+    for (int wd = 0; wd < nw; ++wd) {
+      const uint32_t w = __shfl_sync(0xFFFFFFFFu, x[R == 1 ? 0 : (wd >> 5)], wd & 31);
+      const int p = wd * 32 + lane;
+      if (p < n) c[b * (int64_t)n + p] = (float)((w >> lane) & 1u);
+      if (c_packed && lane == 0) c_packed[b * nw + wd] = w;
+    }
+  }
+}
+
+// ---- helpers ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_bits_kernel(const float *__restrict__ x, int n, int64_t B,
+                                                        uint32_t *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int nw = n < 32 ? 1 : n >> 5;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < B * nw; row += nwarps) {
+    const int64_t b = row / nw;
+    const int wd = (int)(row - b * nw);
+    const int p = wd * 32 + lane;
+    const int bit = (p < n) ? (__ldg(x + b * (int64_t)n + p) != 0.0f) : 0;
+    const uint32_t w = __ballot_sync(0xFFFFFFFFu, bit);
+    if (lane == 0) out[row] = w;
+  }
+}
+__global__ void __launch_bounds__(256) unpack_info_kernel(const uint32_t *__restrict__ packed, const int32_t *__restrict__ pos,
+                                                          int nw, int k, int64_t B, float *__restrict__ out) {
+  const int64_t total = B * (int64_t)k;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / k;
+    const int t = (int)(i - b * k);
+    const int p = __ldg(pos + t);
+    out[i] = (float)((__ldg(packed + b * nw + (p >> 5)) >> (p & 31)) & 1u);
+  }
+}
+
+static unsigned grid_for(int64_t work_items, int per_block, int max_ctas_per_sm = 8) {
+  int64_t g = (work_items + per_block - 1) / per_block;
+  const int64_t cap = (int64_t)device_sm_count() * max_ctas_per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+}  // namespace polar
+
+using namespace polar;
+
+extern "C" int polar_encode_packed(const uint32_t *d_u, int n, int64_t B, uint32_t *d_c, void *stream) {
+  if (!is_pow2(n) || n < 2 || n > POLAR_MAX_N) return set_error(POLAR_EINVAL, "encode: n=%d must be a power of two in [2,%d]", n, POLAR_MAX_N);
+  if (B < 0) return set_error(POLAR_EINVAL, "encode: B < 0");
+  if (B == 0) return POLAR_OK;
+  if (!d_u || !d_c) return set_error(POLAR_EINVAL, "encode: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int m = ilog2(n), nw = POLAR_WORDS(n);
+  if (n <= 1024) {
+    const int64_t total = B * nw;
+    enc_packed_small_kernel<<<grid_for((total + 31) / 32, 8), 256, 0, st>>>(d_u, m, nw, total, d_c);
+  } else if (n == 2048) {
+    enc_packed_kernel<2><<<grid_for(B, 8), 256, 0, st>>>(d_u, m, B, d_c);
+  } else if (n == 4096) {
+    enc_packed_kernel<4><<<grid_for(B, 8), 256, 0, st>>>(d_u, m, B, d_c);
+  } else {
+    enc_packed_kernel<8><<<grid_for(B, 8), 256, 0, st>>>(d_u, m, B, d_c);
+  }
+  count_launch();
+  POLAR_CHECK_LAUNCH("enc_packed");
+  return POLAR_OK;
+}
+
+extern "C" int polar_encode_f32(const float *d_u, const int32_t *d_info_rank, int n, int k, int64_t B, float *d_c,
+                                uint32_t *d_c_packed, void *stream) {
+  if (!is_pow2(n) || n < 2 || n > POLAR_MAX_N) return set_error(POLAR_EINVAL, "encode: n=%d must be a power of two in [2,%d]", n, POLAR_MAX_N);
+  if (B < 0 || k < 0 || k > n) return set_error(POLAR_EINVAL, "encode: bad B/k");
+  if (B == 0) return POLAR_OK;
+  if (!d_u || !d_info_rank || !d_c) return set_error(POLAR_EINVAL, "encode: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int m = ilog2(n);
+  const unsigned g = grid_for(B, 8);
+  if (n <= 1024) enc_f32_kernel<1><<<g, 256, 0, st>>>(d_u, d_info_rank, n, m, k, B, d_c, d_c_packed);
+  else if (n == 2048) enc_f32_kernel<2><<<g, 256, 0, st>>>(d_u, d_info_rank, n, m, k, B, d_c, d_c_packed);
+  else if (n == 4096) enc_f32_kernel<4><<<g, 256, 0, st>>>(d_u, d_info_rank, n, m, k, B, d_c, d_c_packed);
+  else enc_f32_kernel<8><<<g, 256, 0, st>>>(d_u, d_info_rank, n, m, k, B, d_c, d_c_packed);
+  count_launch();
+  POLAR_CHECK_LAUNCH("enc_f32");
+  return POLAR_OK;
+}
+
+extern "C" int polar_pack_bits_f32(const float *d_x, int n, int64_t B, uint32_t *d_packed, void *stream) {
+  if (n < 1 || B < 0 || (n > 32 && (n & 31))) return set_error(POLAR_EINVAL, "pack: n must be <= 32 or a multiple of 32");
+  if (B == 0) return POLAR_OK;
+  if (!d_x || !d_packed) return set_error(POLAR_EINVAL, "pack: null pointer");
+  const int nw = POLAR_WORDS(n);
+  pack_bits_kernel<<<grid_for(B * nw, 8), 256, 0, (cudaStream_t)stream>>>(d_x, n, B, d_packed);
+  count_launch();
+  POLAR_CHECK_LAUNCH("pack_bits");
+  return POLAR_OK;
+}
+
+extern "C" int polar_unpack_info_f32(const uint32_t *d_packed, const int32_t *d_pos, int n, int k, int64_t B,
+                                     float *d_out, void *stream) {
+  if (n < 1 || k < 0 || B < 0) return set_error(POLAR_EINVAL, "unpack: bad sizes");
+  if (B == 0 || k == 0) return POLAR_OK;
+  if (!d_packed || !d_pos || !d_out) return set_error(POLAR_EINVAL, "unpack: null pointer");
+  unpack_info_kernel<<<grid_for(B * (int64_t)k, 256), 256, 0, (cudaStream_t)stream>>>(d_packed, d_pos, POLAR_WORDS(n), k, B, d_out);
+  count_launch();
+  POLAR_CHECK_LAUNCH("unpack_info");
+  return POLAR_OK;
+}

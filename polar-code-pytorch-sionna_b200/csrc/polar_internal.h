@@ -1,0 +1,33 @@
+// polar_internal.h -- host-side plumbing shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "../../include/polar_b200.h"
+
+namespace polar {
+
+int set_error(int code, const char *fmt, ...);      // stores thread-local text, returns code
+void count_launch(int n = 1);                        // gpu_launches accounting
+int env_int(const char *name, int dflt);             // tuning overrides (POLAR_*), read per call
+int device_sm_count();
+int device_max_smem_optin();
+
+inline bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+
+#define POLAR_CHECK_LAUNCH(what)                                                           \
+  do {                                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                                  \
+    if (e__ != cudaSuccess) return polar::set_error(POLAR_ECUDA, "%s: %s", what, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define POLAR_CUDA(call)                                                                   \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) return polar::set_error(POLAR_ECUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+}  // namespace polar

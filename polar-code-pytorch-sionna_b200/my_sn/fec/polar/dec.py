@@ -1,0 +1,85 @@
+"""my_sn decoders (my_sn/fec/polar/dec.py).  Built this round: the CRC-aided SCL decoder
+(dec.py:158-537, selection logic :507-527) on the min-sum list kernel -- the composed oracle of
+SURVEY 8(c) for BASELINE config 3.  The reference's my_sn variant evaluates f with the exact boxplus
+and prunes rate-0/REP nodes; that arithmetic is SURVEY 8(f) row N2 and is NOT built yet (documented in
+DESIGN.md); `use_fast_scl` / `use_hybrid_sc` are accepted and ignored like dec.py:237-238."""
+import numpy as np
+import torch as tc
+from torch import nn
+
+import d_kernels as dk
+from my_sn.fec.crc import CRCEncoder, CRCDecoder
+from polar.polar_sc import SC_Dec  # noqa: F401  (min-sum SC; the boxplus SC of dec.py:13-157 is row N2)
+
+
+class SCL_Dec(nn.Module):
+  def __init__(self, frozen_pos, n, list_size=8, crc_degree=None, use_hybrid_sc=False, use_fast_scl=True,
+               return_crc_status=False, output_dtype=tc.float32, device='cpu'):
+    super().__init__()
+    self.device = device
+    if output_dtype not in (tc.float16, tc.float32, tc.float64):
+      raise ValueError('output_dtype must be {tf.float16, tf.float32, tf.float64}.')
+    self.output_dtype = output_dtype
+    n = int(n)
+    assert len(frozen_pos) <= n, "Num. of elements in frozen_pos cannot be greater than n."
+    assert np.log2(n) == int(np.log2(n)), "n must be a power of 2."
+    assert np.log2(list_size) == int(np.log2(list_size)), "list_size must be a power of 2."
+    self._n = n
+    self._frozen_pos = frozen_pos
+    self._k = self._n - len(self._frozen_pos)
+    self._list_size = int(list_size)
+    self._info_pos = np.setdiff1d(np.arange(self._n), dk.to_numpy_pos(frozen_pos))
+    self._llr_max = 30.
+    assert self._k == len(self._info_pos), "Internal error: invalid info_pos generated."
+    if crc_degree is not None:                                   # dec.py:221-229
+      self._use_crc = True
+      self._crc_decoder = CRCDecoder(CRCEncoder(crc_degree, self._k))
+      self._k_crc = self._crc_decoder._encoder.crc_length
+      self._crc_rows_np = self._crc_decoder._encoder.syndrome_rows(self._info_pos, self._n)
+    else:
+      self._use_crc = False
+      self._k_crc = 0
+      self._crc_rows_np = None
+    assert self._k >= self._k_crc, "Value of k is too small for given CRC_degree."
+    if (crc_degree is None) and return_crc_status:
+      raise ValueError("Returning CRC status requires given crc_degree.")
+    self._return_crc_status = return_crc_status
+    self._crc_rows = {}
+    self.msg_pm = None
+
+  @property
+  def n(self): return self._n
+  @property
+  def k(self): return self._k
+  @property
+  def k_crc(self): return self._k_crc
+  @property
+  def frozen_pos(self): return self._frozen_pos
+  @property
+  def info_pos(self): return self._info_pos
+  @property
+  def llr_max(self): return self._llr_max
+  @property
+  def list_size(self): return self._list_size
+
+  def forward(self, inputs):
+    assert inputs.dtype == self.output_dtype, "Invalid input dtype."
+    assert inputs.shape[-1] == self._n, "Last input dimension must be of length n."
+    assert inputs.dim() > 1
+    dev = inputs.device if inputs.is_cuda else dk.cuda_device(self.device)
+    tables = dk.code_tables(self._frozen_pos, self._n, dev)
+    rows, ln = None, 0
+    if self._use_crc:
+      rows = self._crc_rows.get(str(dev))
+      if rows is None:
+        rows = self._crc_rows[str(dev)] = tc.from_numpy(self._crc_rows_np.view(np.int32).copy()).to(dev)
+      ln = self._k_crc
+    res = dk.scl_decode(inputs, tables, self._list_size, crc_rows=rows, crc_len=ln, want_info=True, want_pm=True)
+    self.msg_pm = res["pm"]
+    output_shape = list(inputs.shape)
+    output_shape[-1] = self.k
+    output_shape[0] = -1
+    out = res["u_info"].reshape(output_shape).to(self.output_dtype)   # CRC bits stay in the output (dec.py:527)
+    if self._return_crc_status:
+      raise Exception('not implement...')                              # dec.py:534-535
+    return out if inputs.is_cuda else out.to(inputs.device)

@@ -1,0 +1,302 @@
+"""d_kernels.py -- loader of the sm_100a kernel library (C ABI, include/polar_b200.h).
+
+In the reference this module holds the *polarization kernel matrices* (x_run_sn_polar/d_kernels.py:3-11:
+`gen_arikan`, `F2`, `F4`..`F32`), star-imported by main.py:30.  Those names are kept.  The B200 build
+also makes it the single place where `libpolar_b200.so` is loaded (ctypes) and where torch tensors
+are turned into raw device pointers: every decoder / encoder / link-model class in this package
+calls the CUDA kernels through the functions below.  There is NO CPU fallback: if the library is
+missing, or no CUDA device is present when a kernel is requested, these functions raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch as tc
+
+from config import device
+
+# ---- polarization kernels (reference d_kernels.py:3-11) -----------------------------------------
+
+
+def gen_arikan(F2, lay):
+  """F2^{(x) lay} (Kronecker power), reference d_kernels.py:3-7."""
+  FN = tc.clone(F2)
+  for _ in range(lay - 1):
+    FN = tc.kron(F2, FN)
+  return FN
+
+
+F2 = tc.tensor([[1, 0], [1, 1]], dtype=tc.float32, device=device)
+F4 = gen_arikan(F2, 2); F8 = gen_arikan(F2, 3)
+F16 = gen_arikan(F2, 4); F32 = gen_arikan(F2, 5)
+
+# ---- library loading ------------------------------------------------------------------------------
+_PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.environ.get("POLAR_B200_LIB", os.path.join(_PKG_DIR, "libpolar_b200.so"))
+_lib = None
+
+POLAR_OK, POLAR_EINVAL, POLAR_EALIGN, POLAR_ENOMEM, POLAR_ECUDA = 0, -1, -2, -3, -4
+SC_MAX_N, SCL_MAX_N, SCL_MAX_L = 8192, 4096, 32
+
+_vp, _i32, _i64, _u64, _f32, _sz = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64,
+                                    ctypes.c_float, ctypes.c_size_t)
+_SIGNATURES = {
+  # name: (restype, argtypes)   -- must match include/polar_b200.h
+  "polar_last_error": (ctypes.c_char_p, []),
+  "polar_version": (ctypes.c_char_p, []),
+  "polar_launch_count": (ctypes.c_ulonglong, []),
+  "polar_sc_decode_f32": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _i32, _vp]),
+  "polar_scl_workspace_bytes": (_sz, [_i32, _i32, _i64]),
+  "polar_scl_decode": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
+  "polar_encode_packed": (_i32, [_vp, _i32, _i64, _vp, _vp]),
+  "polar_encode_f32": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp]),
+  "polar_awgn_frontend": (_i32, [_u64, _u64, _f32, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
+  "polar_qpsk_awgn_llr": (_i32, [_u64, _u64, _f32, _vp, _i32, _i64, _vp, _vp]),
+  "polar_count_errors_packed": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
+  "polar_count_errors_f32": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp]),
+  "polar_pack_bits_f32": (_i32, [_vp, _i32, _i64, _vp, _vp]),
+  "polar_unpack_info_f32": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp]),
+  "polar_sc_decode_host": (_i32, [_vp, _vp, _i32, _i64, _vp, _i32]),
+  "polar_scl_decode_host": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _i32, _i32]),
+}
+
+
+def lib():
+  """The loaded C-ABI library.  Raises (never falls back) when it is missing."""
+  global _lib
+  if _lib is None:
+    if not os.path.exists(LIB_PATH):
+      raise RuntimeError(
+        "polar_b200: %s not found -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(there is no CPU fallback)" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+      fn = getattr(L, name)        # AttributeError if the library does not export a declared symbol
+      fn.restype = res
+      fn.argtypes = args
+    _lib = L
+  return _lib
+
+
+class PolarKernelError(RuntimeError):
+  pass
+
+
+def check(rc):
+  """Turn a POLAR_E* return code into an exception carrying polar_last_error()."""
+  if rc == POLAR_OK:
+    return
+  msg = lib().polar_last_error().decode("utf-8", "replace")
+  if rc == POLAR_EINVAL:
+    raise AssertionError(msg)            # the reference signals bad shapes / sizes with assert
+  if rc == POLAR_ENOMEM:
+    raise MemoryError(msg)
+  raise PolarKernelError("polar_b200 error %d: %s" % (rc, msg))
+
+
+def cuda_device(dev=None):
+  """Resolve the CUDA device kernels run on.  Fails loudly on a machine without a GPU."""
+  if not tc.cuda.is_available():
+    raise RuntimeError("polar_b200: no CUDA device available -- the decoders/encoder/front end run only "
+                       "on the GPU (sm_100a); there is no CPU fallback")
+  if dev is None or str(dev) == "cpu":
+    return tc.device("cuda", tc.cuda.current_device())
+  dev = tc.device(dev)
+  if dev.type != "cuda":
+    raise RuntimeError("polar_b200: device %s is not a CUDA device" % dev)
+  if dev.index is None:
+    dev = tc.device("cuda", tc.cuda.current_device())
+  return dev
+
+
+def ptr(t):
+  return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def stream_ptr(dev):
+  return ctypes.c_void_p(tc.cuda.current_stream(dev).cuda_stream)
+
+
+def words(n):
+  return 1 if n < 32 else n // 32
+
+
+# ---- host-side code description ---------------------------------------------------------------------
+def to_numpy_pos(frozen_pos):
+  """frozen_pos may be a NumPy int array or a torch int64 tensor (main.py passes a tensor)."""
+  if isinstance(frozen_pos, tc.Tensor):
+    return frozen_pos.detach().cpu().numpy().astype(np.int64)
+  return np.asarray(frozen_pos).astype(np.int64)
+
+
+def frozen_mask_words(frozen_pos, n):
+  """uint32[words(n)]: bit (i % 32) of word (i // 32) set <=> position i frozen (as int32 bit pattern)."""
+  f = np.zeros(max(n, 32), dtype=np.uint8)
+  f[to_numpy_pos(frozen_pos)] = 1
+  w = np.packbits(f.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).reshape(-1)
+  return w[:words(n)].copy()
+
+
+class CodeTables:
+  """Device-resident description of one (frozen set, n) code, shared by encoder/decoders/front end."""
+
+  def __init__(self, frozen_pos, n, dev):
+    self.n = int(n)
+    self.dev = dev
+    fp = to_numpy_pos(frozen_pos)
+    self.info_pos_np = np.setdiff1d(np.arange(self.n), fp)          # ascending (polar_sc.py:19)
+    self.k = int(self.info_pos_np.shape[0])
+    self.mask_np = frozen_mask_words(fp, self.n)
+    rank = np.full(self.n, -1, dtype=np.int32)
+    rank[self.info_pos_np] = np.arange(self.k, dtype=np.int32)
+    self.frozen_mask = tc.from_numpy(self.mask_np.view(np.int32).copy()).to(dev)
+    self.info_pos = tc.from_numpy(self.info_pos_np.astype(np.int32)).to(dev)
+    self.info_rank = tc.from_numpy(rank).to(dev)
+    info_mask = (~self.mask_np) & (np.uint32(0xFFFFFFFF) if self.n >= 32 else np.uint32((1 << self.n) - 1))
+    self.info_mask = tc.from_numpy(np.asarray(info_mask, dtype=np.uint32).view(np.int32).copy()).to(dev)
+
+
+_TABLE_CACHE = {}
+
+
+def code_tables(frozen_pos, n, dev):
+  key = (to_numpy_pos(frozen_pos).tobytes(), int(n), str(dev))
+  tb = _TABLE_CACHE.get(key)
+  if tb is None:
+    tb = _TABLE_CACHE[key] = CodeTables(frozen_pos, n, dev)
+  return tb
+
+
+# ---- kernel wrappers (device tensors in, device tensors out) -------------------------------------------
+def _prep_logits(x, n, dev):
+  x = x.to(device=dev, dtype=tc.float32).reshape(-1, n)
+  if not x.is_contiguous() or x.data_ptr() % 16:
+    x = x.contiguous().clone() if x.data_ptr() % 16 else x.contiguous()
+  return x
+
+
+def sc_decode(logits, tables, want_info=True, want_packed=False):
+  """polar_sc_decode_f32.  logits [B,n] (any float dtype/device) -> (u_info fp32 [B,k] | None, u_packed int32 | None)."""
+  dev = tables.dev
+  x = _prep_logits(logits, tables.n, dev)
+  B = x.shape[0]
+  u_info = tc.empty((B, tables.k), dtype=tc.float32, device=dev) if want_info else None
+  u_packed = tc.empty((B, words(tables.n)), dtype=tc.int32, device=dev) if want_packed else None
+  with tc.cuda.device(dev):
+    check(lib().polar_sc_decode_f32(ptr(x), ptr(tables.frozen_mask), tables.n, B, ptr(u_packed), ptr(u_info),
+                                    ptr(tables.info_pos), tables.k, stream_ptr(dev)))
+  return u_info, u_packed
+
+
+_WS_CACHE = {}
+
+
+def scl_decode(logits, tables, list_size, crc_rows=None, crc_len=0, want_info=True, want_packed=False,
+               want_pm=False, want_list=False):
+  """polar_scl_decode -> dict(u_info, u_packed, pm [B,L] fp64, list [B,L,words] int32)."""
+  dev = tables.dev
+  x = _prep_logits(logits, tables.n, dev)
+  B, n, L = x.shape[0], tables.n, int(list_size)
+  out = {"u_info": None, "u_packed": None, "pm": None, "list": None}
+  if want_info:
+    out["u_info"] = tc.empty((B, tables.k), dtype=tc.float32, device=dev)
+  if want_packed:
+    out["u_packed"] = tc.empty((B, words(n)), dtype=tc.int32, device=dev)
+  if want_pm:
+    out["pm"] = tc.empty((B, L), dtype=tc.float64, device=dev)
+  if want_list:
+    out["list"] = tc.empty((B, L, words(n)), dtype=tc.int32, device=dev)
+  with tc.cuda.device(dev):
+    need = int(lib().polar_scl_workspace_bytes(n, L, B)) if B > 0 else 0
+    ws = None
+    if need:
+      ws = _WS_CACHE.get(str(dev))
+      if ws is None or ws.numel() < need:
+        ws = _WS_CACHE[str(dev)] = tc.empty(need + 256, dtype=tc.uint8, device=dev)
+    check(lib().polar_scl_decode(ptr(x), ptr(tables.frozen_mask), n, L, B, ptr(out["u_packed"]), ptr(out["u_info"]),
+                                 ptr(tables.info_pos), tables.k, ptr(out["pm"]), ptr(out["list"]),
+                                 ptr(crc_rows), int(crc_len), ptr(ws), need, stream_ptr(dev)))
+  return out
+
+
+def encode_f32(u, tables, want_packed=False):
+  """polar_encode_f32: u [B,k] 0/1 -> c [B,n] fp32 (and optionally the packed codeword)."""
+  dev = tables.dev
+  u = u.to(device=dev, dtype=tc.float32).reshape(-1, tables.k).contiguous()
+  B = u.shape[0]
+  c = tc.empty((B, tables.n), dtype=tc.float32, device=dev)
+  cp = tc.empty((B, words(tables.n)), dtype=tc.int32, device=dev) if want_packed else None
+  with tc.cuda.device(dev):
+    check(lib().polar_encode_f32(ptr(u), ptr(tables.info_rank), tables.n, tables.k, B, ptr(c), ptr(cp), stream_ptr(dev)))
+  return (c, cp) if want_packed else c
+
+
+def encode_packed(u_full_packed, n):
+  dev = u_full_packed.device
+  x = u_full_packed.contiguous()
+  out = tc.empty_like(x)
+  with tc.cuda.device(dev):
+    check(lib().polar_encode_packed(ptr(x), int(n), x.shape[0], ptr(out), stream_ptr(dev)))
+  return out
+
+
+def awgn_frontend(tables, batch_size, no, seed, offset=0, want_codeword=False):
+  """polar_awgn_frontend -> (u_packed int32 [B,words], c_packed | None, logits fp32 [B,n])."""
+  dev = tables.dev
+  B, n = int(batch_size), tables.n
+  u = tc.empty((B, words(n)), dtype=tc.int32, device=dev)
+  c = tc.empty((B, words(n)), dtype=tc.int32, device=dev) if want_codeword else None
+  logit = tc.empty((B, n), dtype=tc.float32, device=dev)
+  with tc.cuda.device(dev):
+    check(lib().polar_awgn_frontend(int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset), float(no), ptr(tables.frozen_mask), n, B,
+                                    ptr(u), ptr(c), ptr(logit), stream_ptr(dev)))
+  return u, c, logit
+
+
+def qpsk_awgn_llr(c, no, seed, offset=0):
+  dev = c.device
+  c2 = c.to(tc.float32).reshape(-1, c.shape[-1]).contiguous()
+  out = tc.empty_like(c2)
+  with tc.cuda.device(dev):
+    check(lib().polar_qpsk_awgn_llr(int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset), float(no), ptr(c2), c2.shape[1], c2.shape[0],
+                                    ptr(out), stream_ptr(dev)))
+  return out.reshape(c.shape)
+
+
+def unpack_info(packed, pos, n):
+  dev = packed.device
+  B, k = packed.shape[0], pos.shape[0]
+  out = tc.empty((B, k), dtype=tc.float32, device=dev)
+  with tc.cuda.device(dev):
+    check(lib().polar_unpack_info_f32(ptr(packed.contiguous()), ptr(pos), int(n), k, B, ptr(out), stream_ptr(dev)))
+  return out
+
+
+def pack_bits(x):
+  dev = x.device
+  x2 = x.to(tc.float32).reshape(-1, x.shape[-1]).contiguous()
+  out = tc.empty((x2.shape[0], words(x2.shape[1])), dtype=tc.int32, device=dev)
+  with tc.cuda.device(dev):
+    check(lib().polar_pack_bits_f32(ptr(x2), x2.shape[1], x2.shape[0], ptr(out), stream_ptr(dev)))
+  return out
+
+
+def count_errors_f32(b, b_hat, counters):
+  """counters: int64[2] device tensor, += (bit errors, block errors)."""
+  dev = counters.device
+  k = b.shape[-1]
+  b2 = b.to(device=dev, dtype=tc.float32).reshape(-1, k).contiguous()
+  h2 = b_hat.to(device=dev, dtype=tc.float32).reshape(-1, k).contiguous()
+  with tc.cuda.device(dev):
+    check(lib().polar_count_errors_f32(ptr(b2), ptr(h2), k, b2.shape[0], ptr(counters), stream_ptr(dev)))
+
+
+def count_errors_packed(a, b, mask, n, counters):
+  dev = counters.device
+  with tc.cuda.device(dev):
+    check(lib().polar_count_errors_packed(ptr(a.contiguous()), ptr(b.contiguous()), ptr(mask), int(n), a.shape[0],
+                                          ptr(counters), stream_ptr(dev)))
+
+
+def launch_count():
+  return int(lib().polar_launch_count())

@@ -1,0 +1,198 @@
+"""GPU parity tests: the CUDA path (through the Python mirror -> ctypes -> C ABI) against the golden
+fixtures produced by the unmodified reference and against the CPU oracle on fresh seeded inputs.
+Bar: bit-exact decisions; SCL path metrics within 1e-5 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from util import golden, golden_names, unpack_words, pack_words, awgn_logits
+
+pytestmark = pytest.mark.gpu
+PM_RTOL = 1e-5   # north_star tolerance for SCL path metrics
+
+
+def _dk():
+    import d_kernels as dk
+    return dk
+
+
+@pytest.mark.parametrize("name", golden_names("sc_"))
+def test_sc_matches_reference_golden(name):
+    import torch
+    from polar.polar_sc import SC_Dec
+    d = golden(name)
+    n = d["logits"].shape[1]
+    dec = SC_Dec(d["frozen_pos"], n)
+    out = dec(torch.from_numpy(d["logits"]).cuda())
+    assert out.dtype == torch.float32 and out.shape == (d["logits"].shape[0], dec.k)
+    assert np.array_equal(out.cpu().numpy().astype(np.uint8), d["u_hat"])
+
+
+@pytest.mark.parametrize("n,k,B,ebno", [(2, 1, 257, 3.0), (4, 2, 1000, 3.0), (8, 4, 1000, 2.0), (32, 16, 4099, 2.0),
+                                        (64, 32, 5000, 1.0), (128, 64, 3001, 2.0), (512, 256, 2000, 3.0),
+                                        (1024, 512, 4096, 4.0), (2048, 1024, 600, 4.0), (4096, 2048, 300, 4.5),
+                                        (8192, 4096, 70, 5.0)])
+def test_sc_matches_oracle_random(n, k, B, ebno):
+    import torch
+    from oracle import polar_oracle as po, c_oracle as co
+    dk = _dk()
+    fp = po.rm_frozen_pos(n, n - k)
+    rng = np.random.default_rng(n + k)
+    _, logits = awgn_logits(rng, n, k, fp, B, ebno)
+    logits[::7] = np.round(logits[::7])            # quantised rows: exact zeros and ties
+    ref = co.sc_decode_full(logits, po.frozen_vec(fp, n))
+    tables = dk.code_tables(fp, n, torch.device("cuda", 0))
+    u_info, u_packed = dk.sc_decode(torch.from_numpy(logits).cuda(), tables, want_info=True, want_packed=True)
+    got = unpack_words(u_packed.cpu().numpy(), n)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(u_info.cpu().numpy().astype(np.uint8), ref[:, po.info_positions(fp, n)])
+
+
+@pytest.mark.parametrize("cw", [1, 2, 4, 8, 16, 32])
+def test_sc_all_codewords_per_warp_variants(cw, monkeypatch):
+    import torch
+    from oracle import polar_oracle as po, c_oracle as co
+    dk = _dk()
+    n, k, B = 256, 128, 1111
+    monkeypatch.setenv("POLAR_SC_CW", str(cw))
+    fp = po.rm_frozen_pos(n, n - k)
+    _, logits = awgn_logits(np.random.default_rng(cw), n, k, fp, B, 2.0)
+    ref = co.sc_decode_full(logits, po.frozen_vec(fp, n))
+    tables = dk.code_tables(fp, n, torch.device("cuda", 0))
+    _, u_packed = dk.sc_decode(torch.from_numpy(logits).cuda(), tables, want_info=False, want_packed=True)
+    assert np.array_equal(unpack_words(u_packed.cpu().numpy(), n), ref)
+
+
+def test_sc_extreme_frozen_patterns():
+    """all-frozen, none-frozen, single info bit, alternating: exercises rate-0 / rate-1 shortcuts."""
+    import torch
+    from oracle import polar_oracle as po, c_oracle as co
+    dk = _dk()
+    n, B = 256, 777
+    rng = np.random.default_rng(5)
+    logits = (rng.standard_normal((B, n)) * 4).astype(np.float32)
+    logits[::5] = np.round(logits[::5])
+    for fp in (np.arange(n), np.arange(0), np.arange(n - 1), np.arange(0, n, 2), np.arange(n // 2),
+               np.arange(n // 2, n), np.concatenate([np.arange(32), np.arange(64, 96)])):
+        ref = co.sc_decode_full(logits, po.frozen_vec(fp, n))
+        tables = dk.code_tables(fp, n, torch.device("cuda", 0))
+        _, u_packed = dk.sc_decode(torch.from_numpy(logits).cuda(), tables, want_info=False, want_packed=True)
+        assert np.array_equal(unpack_words(u_packed.cpu().numpy(), n), ref), len(fp)
+
+
+def test_sc_api_shapes_dtypes_and_errors():
+    import torch
+    from polar.polar_sc import SC_Dec
+    from oracle import polar_oracle as po
+    fp = po.rm_frozen_pos(16, 8)
+    dec = SC_Dec(torch.from_numpy(fp), 16)            # tensor frozen_pos like main.py
+    x = torch.randn(3, 5, 16, dtype=torch.float64)
+    y = dec(x)                                         # CPU in -> CPU out, any float dtype, 3-D
+    assert y.shape == (3, 5, 8) and y.dtype == torch.float32 and y.device.type == "cpu"
+    want = po.sc_decode(x.numpy().astype(np.float32).reshape(-1, 16), fp, 16).reshape(3, 5, 8)
+    assert np.array_equal(y.numpy(), want)
+    with pytest.raises(AssertionError):
+        dec(torch.randn(4, 8))
+    with pytest.raises(AssertionError):
+        dec(torch.randn(16))
+    assert dec(torch.empty(0, 16)).shape == (0, 8)
+
+
+@pytest.mark.parametrize("name", golden_names("scl_"))
+def test_scl_matches_reference_golden(name):
+    import torch
+    from polar.polar_scl import SCL_Dec
+    dk = _dk()
+    d = golden(name)
+    n = d["logits"].shape[1]
+    L = d["pm"].shape[1]
+    dec = SCL_Dec(d["frozen_pos"], n, list_size=L)
+    out = dec(torch.from_numpy(d["logits"]).cuda())
+    # (i) best-path decisions bit-exact
+    assert np.array_equal(out.cpu().numpy().astype(np.uint8), d["u_best"])
+    # (ii) best path metric within 1e-5 relative
+    pm = dec.msg_pm.cpu().numpy()
+    ref = d["pm"]
+    rel = np.abs(pm[:, 0] - ref[:, 0]) / np.maximum(np.abs(ref[:, 0]), 1e-30)
+    assert rel.max() <= PM_RTOL, rel.max()
+    # (iii) whole list (as a set) + all PMs on the codewords where the oracle variants agree
+    tables = dk.code_tables(d["frozen_pos"], n, torch.device("cuda", 0))
+    res = dk.scl_decode(torch.from_numpy(d["logits"]).cuda(), tables, L, want_list=True, want_pm=True)
+    got_list = unpack_words(res["list"].cpu().numpy(), n)
+    ref_list = np.unpackbits(d["u_list"], axis=-1, bitorder="little")[..., :n]
+    robust = d["robust"]
+    bad = 0
+    for b in np.nonzero(robust)[0]:
+        s_got = set(map(bytes, got_list[b]))
+        s_ref = set(map(bytes, ref_list[b]))
+        bad += (s_got != s_ref)
+        relb = np.abs(pm[b] - ref[b]) / np.maximum(np.abs(ref[b]), 1e-30)
+        assert relb.max() <= PM_RTOL
+    assert bad == 0, "%d of %d robust lists differ" % (bad, int(robust.sum()))
+
+
+@pytest.mark.parametrize("n,k,L,B,ebno", [(8, 4, 2, 300, 2.0), (16, 8, 4, 300, 2.0), (32, 16, 8, 300, 2.0), (64, 32, 8, 400, 1.0),
+                                          (128, 64, 16, 200, 2.0), (256, 128, 32, 100, 2.5), (512, 256, 8, 200, 3.0),
+                                          (1024, 512, 8, 256, 3.0), (1024, 512, 32, 64, 3.0), (2048, 1024, 32, 24, 3.5),
+                                          (2048, 1024, 8, 64, 3.5), (4096, 2048, 4, 32, 4.0), (1024, 512, 1, 128, 3.0)])
+def test_scl_matches_oracle_random(n, k, L, B, ebno):
+    import torch
+    from oracle import polar_oracle as po, c_oracle as co
+    dk = _dk()
+    fp = po.rm_frozen_pos(n, n - k)
+    rng = np.random.default_rng(1000 + n + L)
+    _, logits = awgn_logits(rng, n, k, fp, B, ebno)
+    u_ref, pm_ref = co.scl_decode_full(logits, po.frozen_vec(fp, n), L)
+    tables = dk.code_tables(fp, n, torch.device("cuda", 0))
+    res = dk.scl_decode(torch.from_numpy(logits).cuda(), tables, L, want_packed=True, want_pm=True, want_info=True)
+    got = unpack_words(res["u_packed"].cpu().numpy(), n)
+    assert np.array_equal(got, u_ref[:, 0, :])
+    pm = res["pm"].cpu().numpy()
+    rel = np.abs(pm[:, 0] - pm_ref[:, 0]) / np.maximum(np.abs(pm_ref[:, 0]), 1e-30)
+    assert rel.max() <= PM_RTOL
+    assert np.array_equal(res["u_info"].cpu().numpy().astype(np.uint8), u_ref[:, 0][:, po.info_positions(fp, n)])
+
+
+def test_scl_api_errors_and_shapes():
+    import torch
+    from polar.polar_scl import SCL_Dec
+    from oracle import polar_oracle as po
+    fp = po.rm_frozen_pos(16, 8)
+    with pytest.raises(AssertionError):
+        SCL_Dec(fp, 16, list_size=3)
+    with pytest.raises(ValueError):
+        SCL_Dec(fp, 16, output_dtype=torch.int32)
+    dec = SCL_Dec(fp, 16, list_size=32)               # more paths than codewords is legal
+    with pytest.raises(AssertionError, match="Invalid input dtype"):
+        dec(torch.randn(4, 16, dtype=torch.float64))
+    x = torch.randn(3, 5, 16)
+    y = dec(x)
+    assert y.shape == (3, 5, 8) and y.device.type == "cpu"
+    assert np.array_equal(y.numpy(), po.scl_decode(x.numpy().reshape(-1, 16), fp, 16, 32).reshape(3, 5, 8))
+
+
+def test_encoder_matches_reference_golden():
+    import torch
+    from polar.enc import PolarEncoder
+    d = golden("enc")
+    fz = golden("frozen_sets")
+    for n in (8, 64, 256, 1024, 4096):
+        fp = fz["rm_%d_%d" % (n, n // 2)]
+        enc = PolarEncoder(fp, n, None)
+        c = enc(torch.from_numpy(d["u_%d" % n].astype(np.float32)).cuda())
+        assert c.dtype == torch.float32
+        assert np.array_equal(c.cpu().numpy().astype(np.uint8), d["c_%d" % n]), n
+
+
+@pytest.mark.parametrize("n", [2, 4, 16, 32, 64, 512, 1024, 2048, 4096, 8192])
+def test_encode_packed_matches_oracle_and_is_involution(n):
+    import torch
+    from oracle import c_oracle as co
+    dk = _dk()
+    rng = np.random.default_rng(n)
+    B = 513
+    u = rng.integers(0, 2, size=(B, n)).astype(np.uint8)
+    ref = co.polar_transform(u)
+    up = torch.from_numpy(pack_words(u).view(np.int32)).cuda()
+    cp = dk.encode_packed(up, n)
+    assert np.array_equal(unpack_words(cp.cpu().numpy(), n), ref)
+    assert torch.equal(dk.encode_packed(cp, n), up)           # G is an involution over GF(2)
