@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the polar-code hot path on B200 (contract: see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): SC decoder, k=512 n=1024 RM-rule code, AWGN/BPSK at Eb/N0 = 4 dB,
+batch B = 2^20 codewords per GPU (4 GiB of fp32 logits, larger than the 126 MB L2), synthetic, generated
+on the device by polar_awgn_frontend.  One step = one decode of the whole batch.
+  value : decoded information Gbit/s, whole job (all ranks), inputs resident in HBM, CUDA-event timed.
+  e2e   : same metric through the host-buffer C-ABI call polar_sc_decode_host (pinned host logits ->
+          chunked H2D + decode + D2H of the packed decisions inside the timed region).
+  scl8  : the same two numbers for SCL L=8 + CRC11 (configs[2], B = 2^18), reported beside the headline.
+--impl reference: the CPU restatement of the reference (oracle/libpolar_oracle.so, all host threads) on a
+bounded sample per step (the reference itself is pure Python and cannot travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "polar-code-pytorch-sionna_b200")
+for p in (ROOT, PKG, os.path.join(PKG, "x_run_sn_polar")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+N_CODE, K_CODE, EBNO_DB = 1024, 512, 4.0
+SC_BATCH = 1 << 20
+SCL_L, SCL_BATCH, SCL_CRC, SCL_EBNO_DB = 8, 1 << 18, "CRC11", 3.0
+
+
+def frozen_set(n, k):
+    """RM-rule frozen set of the reference (froze.py:4-16); golden fixture first (host-independent)."""
+    path = os.path.join(ROOT, "tests", "golden", "frozen_sets.npz")
+    key = "rm_%d_%d" % (n, k)
+    if os.path.exists(path):
+        d = np.load(path)
+        if key in d:
+            return d[key]
+    from oracle import polar_oracle as po
+    return po.rm_frozen_pos(n, n - k)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in self.rows:
+            for i, nm in enumerate(names):
+                if len(r) > 4 + i and r[4 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(kind, logits_np, frozen, L=0, seconds_hint=10.0):
+    """Time the C oracle (all host threads) on a bounded sample; returns (cw/s, threads, n_codewords)."""
+    from oracle import c_oracle as co
+    co.build()
+    thr = co.num_threads()
+    t0 = time.perf_counter()
+    if kind == "sc":
+        co.sc_decode_full(logits_np, frozen)
+    else:
+        co.scl_decode_full(logits_np, frozen, L)
+    dt = time.perf_counter() - t0
+    return logits_np.shape[0] / dt, thr, logits_np.shape[0]
+
+
+def run_reference(args):
+    """--impl reference: CPU restatement of the reference path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import polar_oracle as po, c_oracle as co
+    co.build()
+    fp = frozen_set(N_CODE, K_CODE)
+    fz = po.frozen_vec(fp, N_CODE)
+    sample = 1 << 16
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import awgn_logits
+    _, logits = awgn_logits(np.random.default_rng(1234), N_CODE, K_CODE, fp, sample, EBNO_DB)
+    for _ in range(args.warmup):
+        co.sc_decode_full(logits, fz)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        co.sc_decode_full(logits, fz)
+    dt = time.perf_counter() - t0
+    cws = sample * args.steps / dt
+    val = cws * K_CODE / 1e9
+    line = {"impl": "reference", "metric": "decoded_info_throughput_sc_n1024", "value": val, "unit": "Gbit/s",
+            "codewords_per_s": cws, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SC k=512 n=1024 AWGN BPSK Eb/N0=4dB (configs[1]); CPU restatement of the reference "
+                                   "(oracle/polar_oracle.c, the Python reference cannot travel), %d-codeword sample per step" % sample},
+            "cpu_baseline": {"value": val, "unit": "Gbit/s", "cores": co.num_threads(), "kind": "port",
+                             "sample": "%d codewords per step x %d steps" % (sample, args.steps)},
+            "e2e": {"value": val, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=SC_BATCH, help="SC codewords per GPU per step")
+    ap.add_argument("--skip-scl", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import d_kernels as dk
+    from oracle import polar_oracle as po      # checker + cpu_baseline leg only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    n, k, B = N_CODE, K_CODE, args.batch
+    fp = frozen_set(n, k)
+    tables = dk.code_tables(fp, n, dev)
+    no = po.ebnodb2no(EBNO_DB, 2, k / n)
+    nw = dk.words(n)
+    # ---- inputs resident in HBM before timing (front-end kernel, seed 1234 + rank) --------------------
+    u_tx, _, logits = dk.awgn_frontend(tables, B, no, 1234 + rank)
+    u_hat = torch.empty((B, nw), dtype=torch.int32, device=dev)
+    stream = dk.stream_ptr(dev)
+    lib = dk.lib()
+
+    def sc_step():
+        dk.check(lib.polar_sc_decode_f32(dk.ptr(logits), dk.ptr(tables.frozen_mask), n, B, dk.ptr(u_hat), None, None, 0, stream))
+
+    for _ in range(args.warmup):
+        sc_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = dk.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_all0.record()
+    for a, b in evs:
+        a.record(); sc_step(); b.record()
+    t_all1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = dk.launch_count() - launches0
+    total_ms = max_over_ranks(t_all0.elapsed_time(t_all1))
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))      # one launch per step: the SC kernel itself
+    ms_per_step = total_ms / args.steps
+    cws = world * B / (ms_per_step * 1e-3)
+    value = cws * k / 1e9
+
+    # ---- parity spot check in the same run (bit-exact vs the oracle on a slice; BLER sanity) ------------
+    parity = None
+    if rank == 0:
+        from oracle import c_oracle as co
+        co.build()
+        m_chk = 4096
+        ref = co.sc_decode_full(logits[:m_chk].cpu().numpy(), po.frozen_vec(fp, n))
+        got = np.unpackbits(u_hat[:m_chk].cpu().numpy().view(np.uint8), axis=-1, bitorder="little")[:, :n]
+        cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+        dk.count_errors_packed(u_tx, u_hat, tables.info_mask, n, cnt)
+        c = cnt.cpu().numpy()
+        parity = {"bit_exact_vs_oracle": bool(np.array_equal(got, ref)), "checked_codewords": m_chk,
+                  "bler": float(c[1]) / B, "ber": float(c[0]) / (B * k)}
+
+    # ---- end to end: pinned host logits -> polar_sc_decode_host (H2D + decode + D2H in the timed region)
+    e2e = None
+    if not args.skip_e2e:
+        h_logits = torch.empty((B, n), dtype=torch.float32, pin_memory=True)
+        h_logits.copy_(logits)
+        h_out = torch.empty((B, nw), dtype=torch.int32, pin_memory=True)
+        mask_np = tables.mask_np
+
+        def e2e_step():
+            dk.check(lib.polar_sc_decode_host(h_logits.data_ptr(), mask_np.ctypes.data, n, B, h_out.data_ptr(), local))
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(3, min(args.steps, 5))
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
+        ok = bool(torch.equal(h_out[:4096], u_hat[:4096].cpu()))
+        e2e = {"value": world * B / (e2e_ms * 1e-3) * k / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": B * n * 4,
+               "d2h_bytes_per_step": B * nw * 4, "ms_per_step": e2e_ms, "codewords_per_s": world * B / (e2e_ms * 1e-3),
+               "api": "polar_sc_decode_host (pinned host buffers, 2-stream chunked copy/compute overlap)",
+               "matches_device_path": ok}
+        del h_logits, h_out
+
+    # ---- SCL L=8 + CRC11 (configs[2]) ------------------------------------------------------------------
+    scl = None
+    if not args.skip_scl:
+        from my_sn.fec.crc import CRCEncoder
+        Bs = SCL_BATCH
+        crc_chk = CRCEncoder(SCL_CRC, k)                       # validity check spans all k decoder outputs (dec.py:508-516)
+        crc = CRCEncoder(SCL_CRC, k - crc_chk.crc_length)      # generator for the payload
+        rows = torch.from_numpy(crc_chk.syndrome_rows(tables.info_pos_np, n).view(np.int32).copy()).to(dev)
+        no_s = po.ebnodb2no(SCL_EBNO_DB, 2, k / n)
+        # payload + CRC parity -> polar codeword -> channel, all on the device (untimed set-up)
+        payload = torch.randint(0, 2, (Bs, k - crc.crc_length), device=dev, dtype=torch.float32)
+        bits = crc(payload)
+        cw = dk.encode_f32(bits, tables)
+        lg = dk.qpsk_awgn_llr(cw, no_s, 4321 + rank)
+        best = torch.empty((Bs, nw), dtype=torch.int32, device=dev)
+        need = int(lib.polar_scl_workspace_bytes(n, SCL_L, Bs))
+        ws = torch.empty(max(need, 256) + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+
+        def scl_step():
+            dk.check(lib.polar_scl_decode(dk.ptr(lg), dk.ptr(tables.frozen_mask), n, SCL_L, Bs, dk.ptr(best), None, None, 0,
+                                          None, None, dk.ptr(rows), crc.crc_length, ws_ptr, need, stream))
+        scl_steps = max(3, min(args.steps, 5))
+        for _ in range(2):
+            scl_step()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = dk.launch_count()
+        a.record()
+        for _ in range(scl_steps):
+            scl_step()
+        b.record()
+        barrier()
+        launches += dk.launch_count() - l0
+        scl_ms = max_over_ranks(a.elapsed_time(b) / scl_steps)
+        scl_cws = world * Bs / (scl_ms * 1e-3)
+        tx = dk.pack_bits(bits)
+        cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+        txu = torch.zeros((Bs, nw), dtype=torch.int32, device=dev)
+        # transmitted u (info bits scattered): decode of a noiseless codeword is the cheapest way to get it packed
+        full = torch.zeros((Bs, n), dtype=torch.float32, device=dev)
+        full[:, tables.info_pos.long()] = bits
+        txu = dk.pack_bits(full)
+        dk.count_errors_packed(txu, best, tables.info_mask, n, cnt)
+        c = cnt.cpu().numpy()
+        scl = {"metric": "decoded_info_throughput_scl8_crc11_n1024", "value": scl_cws * k / 1e9, "unit": "Gbit/s",
+               "codewords_per_s": scl_cws, "ms_per_step": scl_ms, "batch": Bs, "ebno_db": SCL_EBNO_DB,
+               "bler": float(c[1]) / Bs, "workload": "SCL L=8 k=512 (501+CRC11) n=1024 CRC-aided selection, batch 256K (configs[2])"}
+        if not args.skip_e2e:
+            h_lg = torch.empty((Bs, n), dtype=torch.float32, pin_memory=True)
+            h_lg.copy_(lg)
+            h_best = torch.empty((Bs, nw), dtype=torch.int32, pin_memory=True)
+            rows_np = crc_chk.syndrome_rows(tables.info_pos_np, n)
+
+            def scl_e2e():
+                dk.check(lib.polar_scl_decode_host(h_lg.data_ptr(), tables.mask_np.ctypes.data, n, SCL_L, Bs, h_best.data_ptr(), None,
+                                                   rows_np.ctypes.data, crc.crc_length, local))
+            scl_e2e()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                scl_e2e()
+            torch.cuda.synchronize()
+            ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / 3)
+            scl["e2e"] = {"value": world * Bs / (ms * 1e-3) * k / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": Bs * n * 4,
+                          "d2h_bytes_per_step": Bs * nw * 4, "ms_per_step": ms,
+                          "matches_device_path": bool(torch.equal(h_best[:2048], best[:2048].cpu()))}
+        if rank == 0 and not args.skip_cpu:
+            smp = 4096
+            rate, thr, cnt_cw = cpu_oracle_rate("scl", lg[:smp].cpu().numpy(), po.frozen_vec(fp, n), SCL_L)
+            scl["cpu_baseline"] = {"value": rate * k / 1e9, "unit": "Gbit/s", "codewords_per_s": rate, "cores": thr, "kind": "port",
+                                   "sample": "first %d codewords of the GPU batch, C restatement (oracle/polar_oracle.c)" % cnt_cw}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks, peak_src = measured_peaks()
+    bytes_per_cw = 4 * n + k // 8           # fp32 logits in, bit-packed decisions out (k info bits)
+    achieved = B * bytes_per_cw / (kern_ms * 1e-3) / 1e9
+    cpu = None
+    if not args.skip_cpu:
+        smp = 1 << 18
+        rate, thr, cnt_cw = cpu_oracle_rate("sc", logits[:smp].cpu().numpy(), po.frozen_vec(fp, n))
+        cpu = {"value": rate * k / 1e9, "unit": "Gbit/s", "codewords_per_s": rate, "cores": thr, "kind": "port",
+               "sample": "first %d codewords of the GPU batch, C restatement of the reference (oracle/polar_oracle.c); "
+                         "the Python reference itself measured 3270 cw/s on 8 vCPU (BASELINE.md)" % cnt_cw}
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "sc_traffic_bytes_per_launch.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    line = {
+        "metric": "decoded_info_throughput_sc_n1024", "value": value, "unit": "Gbit/s", "codewords_per_s": cws,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "SC k=512 n=1024 RM-rule code, AWGN BPSK Eb/N0=4dB, batch %d codewords per GPU (configs[1])" % B,
+                   "l2": "inputs (%.1f GiB per GPU) larger than L2, no flush needed" % (B * n * 4 / 2 ** 30),
+                   "parallelism": "batch sharded over %d rank(s), no data-path collective" % world},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "sc_tree_kernel", "kernel_ms": kern_ms, "bytes_per_codeword": bytes_per_cw,
+                     "note": "binding bound is FP32/INT issue + shared memory, not HBM (DESIGN.md)"},
+        "cpu_baseline": cpu, "parity": parity, "scl8": scl,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

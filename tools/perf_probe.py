@@ -1,0 +1,74 @@
+"""Quick kernel timing sweep (CUDA events) for tuning; not the bench.  Usage on the GPU box:
+   python tools/perf_probe.py sc|scl|fe [n] [B]"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "polar-code-pytorch-sionna_b200")
+for p in (ROOT, PKG, os.path.join(PKG, "x_run_sn_polar")):
+    sys.path.insert(0, p)
+import numpy as np
+import torch
+
+import d_kernels as dk
+from oracle import polar_oracle as po
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return min(ts), float(np.median(ts))
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else "sc"
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+    k = n // 2
+    dev = torch.device("cuda", 0)
+    fp = po.rm_frozen_pos(n, n - k)
+    tables = dk.code_tables(fp, n, dev)
+    no = po.ebnodb2no(4.0, 2, k / n)
+    if what == "sc":
+        B = int(sys.argv[3]) if len(sys.argv) > 3 else (1 << 28) // n
+        _, _, x = dk.awgn_frontend(tables, B, no, 1234)
+        up = torch.empty((B, dk.words(n)), dtype=torch.int32, device=dev)
+        for cw in [int(v) for v in os.environ.get("CWS", "2,4,8,16,32").split(",")]:
+            for warps in [int(v) for v in os.environ.get("WARPS", "1,2,4").split(",")]:
+                os.environ["POLAR_SC_CW"] = str(cw); os.environ["POLAR_SC_WARPS"] = str(warps)
+                try:
+                    f = lambda: dk.check(dk.lib().polar_sc_decode_f32(dk.ptr(x), dk.ptr(tables.frozen_mask), n, B, dk.ptr(up), None, None, 0, dk.stream_ptr(dev)))
+                    best, med = timeit(f)
+                    print("SC n=%d B=%d CW=%2d warps=%d: %8.3f ms  %.3e cw/s  %.1f Gbit/s info  HBM-frac %.3f" %
+                          (n, B, cw, warps, best, B / best * 1e3, B / best * 1e3 * k / 1e9, B / best * 1e3 * (4 * n + k / 8) / 6552.3e9), flush=True)
+                except Exception as e:
+                    print("SC CW=%d warps=%d failed: %s" % (cw, warps, e))
+    elif what == "scl":
+        L = int(os.environ.get("L", "8"))
+        B = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 15
+        _, _, x = dk.awgn_frontend(tables, B, no, 1234)
+        for kb in [int(v) for v in os.environ.get("KBS", "72,40,24,12").split(",")]:
+            for warps in [int(v) for v in os.environ.get("WARPS", "1,2,4").split(",")]:
+                os.environ["POLAR_SCL_SMEM_KB"] = str(kb); os.environ["POLAR_SCL_WARPS"] = str(warps)
+                try:
+                    f = lambda: dk.scl_decode(x, tables, L, want_packed=True, want_info=False)
+                    best, med = timeit(f, iters=3, warm=1)
+                    print("SCL L=%d n=%d B=%d smemKB=%d warps=%d: %8.3f ms  %.3e cw/s  %.3f Gbit/s info" %
+                          (L, n, B, kb, warps, best, B / best * 1e3, B / best * 1e3 * k / 1e9), flush=True)
+                except Exception as e:
+                    print("SCL kb=%d warps=%d failed: %s" % (kb, warps, e))
+    elif what == "fe":
+        B = int(sys.argv[3]) if len(sys.argv) > 3 else (1 << 28) // n
+        f = lambda: dk.awgn_frontend(tables, B, no, 1234)
+        best, med = timeit(f)
+        print("frontend n=%d B=%d: %.3f ms  %.3e cw/s  write %.1f GB/s" % (n, B, best, B / best * 1e3, B * n * 4 / best * 1e3 / 1e9))
+
+
+if __name__ == "__main__":
+    main()
