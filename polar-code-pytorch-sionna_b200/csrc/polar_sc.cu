@@ -240,6 +240,186 @@ __global__ void __launch_bounds__(256) sc_tree_kernel(const float *__restrict__ 
   (void)LOGCW;
 }
 
+
+// ------------------------------------------------------------------ n >= 64: CTA per `cw` codewords
+// Same algorithm as sc_tree_kernel, different mapping: ALL warps of the CTA cooperate on the wide
+// (stage >= 5) f/g/merge steps of `cw` <= 32 codewords, and ONE warp then decodes the 32-leaf subtrees
+// with one lane per codeword.  The bottom phase issues the same ~800 instructions whether 8 or 32 lanes
+// are active, so putting up to 32 codewords behind one bottom warp cuts the issue slots per codeword
+// ~3x versus the warp-per-8-codewords mapping, while shared memory (4.2 KB per codeword) still lets
+// two CTAs share an SM and overlap each other's phases.
+struct ScCtaLayout {
+  int nw, nws, stride;
+  size_t mask_bytes, node_bytes, llr_off, beta_off, uo_off, total;
+};
+__host__ __device__ inline ScCtaLayout sc_cta_layout(int n, int cw) {
+  ScCtaLayout l;
+  l.nw = n >> 5; l.nws = l.nw + 1; l.stride = n - 28;
+  l.mask_bytes = (size_t)((l.nw * 4 + 15) / 16) * 16;
+  l.node_bytes = (size_t)((2 * l.nw + 15) / 16) * 16;
+  l.llr_off = l.mask_bytes + l.node_bytes;
+  l.beta_off = l.llr_off + (size_t)cw * l.stride * 4;
+  l.uo_off = l.beta_off + (size_t)cw * l.nws * 4;
+  l.total = ((l.uo_off + (size_t)cw * l.nws * 4 + 15) / 16) * 16;
+  return l;
+}
+
+template <bool IS_G, bool FROM_GLOBAL>
+__device__ __forceinline__ void sc_top_step(const float *__restrict__ logit, int64_t cw0, int nvalid, int n, float *L,
+                                            const uint32_t *beta, int nws, int stride, int cw, int h, int lgh,
+                                            int left_blk, int tid, int nthr) {
+  // stage 2h -> h : out[j] = f(a[j], a[j+h]) or g(a[j], a[j+h], beta_left[j]), 4 elements per thread
+  const int hq = h >> 2, lq = lgh - 2;
+  float *dst = L + (h - 32);
+  const float *src = L + (2 * h - 32);
+  const int Q = cw * hq;
+  for (int q = tid; q < Q; q += nthr) {
+    const int c = q >> lq, j = (q & (hq - 1)) << 2;
+    float4 a, b;
+    if (FROM_GLOBAL) {
+      const int cl = c < nvalid ? c : nvalid - 1;
+      const float4 *row = reinterpret_cast<const float4 *>(logit + (cw0 + cl) * (int64_t)n);
+      a = __ldg(row + (j >> 2)); b = __ldg(row + ((j + h) >> 2));
+      if (IS_G) {   // LLR = -logit (polar_sc.py:122); for f the negation cancels
+        a.x = -a.x; a.y = -a.y; a.z = -a.z; a.w = -a.w; b.x = -b.x; b.y = -b.y; b.z = -b.z; b.w = -b.w;
+      }
+    } else {
+      a = *reinterpret_cast<const float4 *>(src + c * stride + j);
+      b = *reinterpret_cast<const float4 *>(src + c * stride + j + h);
+    }
+    float4 o;
+    if (IS_G) {
+      const uint32_t bits = beta[c * nws + left_blk + (j >> 5)] >> (j & 31);
+      o.x = g_minsum(a.x, b.x, (bits << 31) & 0x80000000u);
+      o.y = g_minsum(a.y, b.y, (bits << 30) & 0x80000000u);
+      o.z = g_minsum(a.z, b.z, (bits << 29) & 0x80000000u);
+      o.w = g_minsum(a.w, b.w, (bits << 28) & 0x80000000u);
+    } else {
+      o.x = f_minsum(a.x, b.x); o.y = f_minsum(a.y, b.y); o.z = f_minsum(a.z, b.z); o.w = f_minsum(a.w, b.w);
+    }
+    *reinterpret_cast<float4 *>(dst + c * stride + j) = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) sc_cta_kernel(const float *__restrict__ logit,
+                                                     const uint32_t *__restrict__ fmask_g, int n, int cw,
+                                                     int64_t B, int64_t nbatches,
+                                                     uint32_t *__restrict__ u_packed, float *__restrict__ u_info,
+                                                     const int32_t *__restrict__ info_pos, int k) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const ScCtaLayout lay = sc_cta_layout(n, cw);
+  const int m = ilog2(n), nw = lay.nw, nws = lay.nws, stride = lay.stride;
+  uint32_t *fmask = reinterpret_cast<uint32_t *>(smem_raw);
+  unsigned char *nz = smem_raw + lay.mask_bytes;            // nz[(nw >> lv) + (i >> lv)] = node of 2^lv blocks at block i is rate-0
+  float *L = reinterpret_cast<float *>(smem_raw + lay.llr_off);
+  uint32_t *beta = reinterpret_cast<uint32_t *>(smem_raw + lay.beta_off);
+  uint32_t *uo = reinterpret_cast<uint32_t *>(smem_raw + lay.uo_off);
+
+  for (int i = tid; i < nw; i += nthr) {
+    const uint32_t w = __ldg(fmask_g + i);
+    fmask[i] = w; nz[nw + i] = (w == FULLMASK);
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int idx = nw - 1; idx >= 1; --idx) nz[idx] = nz[2 * idx] & nz[2 * idx + 1];
+  __syncthreads();
+
+  for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
+    const int64_t cw0 = batch * cw;
+    const int nvalid = (int)((B - cw0) < (int64_t)cw ? (B - cw0) : (int64_t)cw);
+    int i = 0;
+    while (i < nw) {
+      const int S = (i == 0) ? m : 5 + (__ffs(i) - 1);
+      int s = S;
+      bool zeroed = nz[(nw >> (S - 5)) + (i >> (S - 5))] != 0;
+      if (!zeroed && S < m) {
+        const int h = 1 << S;
+        if (S + 1 == m) sc_top_step<true, true>(logit, cw0, nvalid, n, L, beta, nws, stride, cw, h, S, i - (h >> 5), tid, nthr);
+        else sc_top_step<true, false>(logit, cw0, nvalid, n, L, beta, nws, stride, cw, h, S, i - (h >> 5), tid, nthr);
+        __syncthreads();
+      }
+      while (!zeroed && s > 5) {
+        if (nz[(nw >> (s - 6)) + (i >> (s - 6))]) { zeroed = true; --s; break; }
+        const int h = 1 << (s - 1);
+        if (s == m) sc_top_step<false, true>(logit, cw0, nvalid, n, L, beta, nws, stride, cw, h, s - 1, 0, tid, nthr);
+        else sc_top_step<false, false>(logit, cw0, nvalid, n, L, beta, nws, stride, cw, h, s - 1, 0, tid, nthr);
+        __syncthreads();
+        --s;
+      }
+      const int lv0 = s - 5;
+      if (zeroed) {
+        const int nwd = 1 << lv0;
+        for (int q = tid; q < (cw << lv0); q += nthr) {
+          const int c = q >> lv0, w = q & (nwd - 1);
+          beta[c * nws + i + w] = 0u; uo[c * nws + i + w] = 0u;
+        }
+      } else if (tid < cw) {
+        float x[32];
+        const float4 *src = reinterpret_cast<const float4 *>(L + tid * stride);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 v = src[q];
+          x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+        }
+        uint32_t u;
+        const uint32_t bb = SubTree<5>::run(x, fmask[i], u);
+        beta[tid * nws + i] = bb; uo[tid * nws + i] = u;
+      }
+      __syncthreads();
+      {
+        int lv = lv0, a = i;
+        while (lv < m - 5 && ((a >> lv) & 1)) {
+          const int nwd = 1 << lv, left = a - nwd;
+          for (int q = tid; q < (cw << lv); q += nthr) {
+            const int c = q >> lv, w = q & (nwd - 1);
+            beta[c * nws + left + w] ^= beta[c * nws + a + w];
+          }
+          __syncthreads();
+          a = left; ++lv;
+        }
+      }
+      i += 1 << lv0;
+    }
+    if (u_packed) {
+      for (int q = tid; q < cw * nw; q += nthr) {
+        const int c = q / nw, w = q - c * nw;
+        if (c < nvalid) u_packed[(cw0 + c) * nw + w] = uo[c * nws + w];
+      }
+    }
+    if (u_info) {
+      for (int q = tid; q < nvalid * k; q += nthr) {
+        const int c = q / k, t = q - c * k;
+        const int p = __ldg(info_pos + t);
+        u_info[(cw0 + c) * (int64_t)k + t] = (float)((uo[c * nws + (p >> 5)] >> (p & 31)) & 1u);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static int launch_cta(const float *logit, const uint32_t *fmask, int n, int64_t B, uint32_t *u_packed, float *u_info,
+                      const int32_t *info_pos, int k, int cw, int threads, int ctas_per_sm, cudaStream_t st) {
+  const int max_smem = device_max_smem_optin();
+  if (cw > 32) cw = 32;
+  if (cw < 1) cw = 1;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  // fit `ctas_per_sm` CTAs in the 228 KB of an SM (1 KB reserved per CTA)
+  while (cw > 1 && sc_cta_layout(n, cw).total + 1024 > (size_t)(228 * 1024) / ctas_per_sm) --cw;
+  ScCtaLayout lay = sc_cta_layout(n, cw);
+  if (lay.total > (size_t)max_smem) return set_error(POLAR_ENOMEM, "sc: n=%d needs %zu B shared memory per CTA", n, lay.total);
+  POLAR_CUDA(cudaFuncSetAttribute(sc_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+  const int64_t nbatches = (B + cw - 1) / cw;
+  int64_t grid = nbatches;
+  const int64_t cap = (int64_t)device_sm_count() * ctas_per_sm;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  sc_cta_kernel<<<(unsigned)grid, threads, lay.total, st>>>(logit, fmask, n, cw, B, nbatches, u_packed, u_info, info_pos, k);
+  count_launch();
+  POLAR_CHECK_LAUNCH("sc_cta_kernel");
+  return POLAR_OK;
+}
+
 template <int CW>
 static int launch_tree(const float *logit, const uint32_t *fmask, int n, int64_t B, uint32_t *u_packed,
                        float *u_info, const int32_t *info_pos, int k, int warps, cudaStream_t st) {
@@ -307,6 +487,16 @@ extern "C" int polar_sc_decode_f32(const float *d_logit, const uint32_t *d_froze
       case 16: return launch_small<4>(d_logit, d_frozen_mask, B, d_u_packed, d_u_info_f32, d_info_pos, k, st);
       default: return launch_small<5>(d_logit, d_frozen_mask, B, d_u_packed, d_u_info_f32, d_info_pos, k, st);
     }
+  }
+  if (env_int("POLAR_SC_MODE", 1) == 1) {
+    // CTA mapping (default): up to 32 codewords per CTA, `ctas` CTAs per SM
+    int ctas = env_int("POLAR_SC_CTAS", 3);
+    int threads = env_int("POLAR_SC_THREADS", 256);
+    if (threads < 32) threads = 32;
+    if (threads > 256) threads = 256;
+    threads &= ~31;
+    return launch_cta(d_logit, d_frozen_mask, n, B, d_u_packed, d_u_info_f32, d_info_pos, k,
+                      env_int("POLAR_SC_CTA_CW", 32), threads, ctas, st);
   }
   int cw = env_int("POLAR_SC_CW", sc_default_cw(n));
   int warps = env_int("POLAR_SC_WARPS", 2);

@@ -317,14 +317,14 @@ static SclPlan scl_plan(int n, int L, int64_t B) {
   SclPlan pl;
   const int m = ilog2(n);
   const size_t words = scl_word_count(L, n) * 4;
-  const int budget = env_int("POLAR_SCL_SMEM_KB", 72) * 1024;     // per warp
+  const int budget = env_int("POLAR_SCL_SMEM_KB", 14) * 1024;     // per warp
   int s_glob = m;
   while (s_glob > 0 && scl_llr_smem_doubles(L, s_glob) * 8 + words > (size_t)budget) --s_glob;
   pl.s_glob = s_glob;
   pl.smem_per_warp = ((scl_llr_smem_doubles(L, s_glob) * 8 + words + 15) / 16) * 16;
   pl.ws_doubles_per_warp = (s_glob < m) ? (size_t)L * ((1u << m) - (1u << s_glob)) : 0;
   const int max_smem = device_max_smem_optin();
-  int wpc = env_int("POLAR_SCL_WARPS", 1);
+  int wpc = env_int("POLAR_SCL_WARPS", 2);
   if (wpc < 1) wpc = 1;
   if (wpc > 4) wpc = 4;
   while (wpc > 1 && pl.smem_per_warp * wpc > (size_t)max_smem) --wpc;

@@ -45,8 +45,11 @@ def _dist():
 
 
 def sim_ber(mc_fun, ebno_dbs, batch_size, max_mc_iter, soft_estimates=False, target_bit_errs=None,
-            target_block_errs=None, early_stop=True, verbose=True, dtype=tc.complex64, device='cpu'):
-  """Returns (ber, bler) per SNR point; same stop rules and status codes as sim.py:19-140."""
+            target_block_errs=None, early_stop=True, verbose=True, dtype=tc.complex64, device='cpu', count_fn=None):
+  """Returns (ber, bler) per SNR point; same stop rules and status codes as sim.py:19-140.
+  `count_fn(b, b_hat) -> (bit_errors, block_errors)` defaults to the CUDA counter kernel; it exists so the
+  sharding / stop logic can be exercised with a test double on machines without a GPU."""
+  count_fn = count_fn or _count
   dist = _dist()
   rank0 = dist is None or dist.get_rank() == 0
   verbose = verbose and rank0
@@ -76,7 +79,7 @@ def sim_ber(mc_fun, ebno_dbs, batch_size, max_mc_iter, soft_estimates=False, tar
       b, b_hat = mc_fun(batch_size=batch_size, ebno_db=ebno_dbs[i])[:2]
       if soft_estimates:
         b_hat = hard_decisions(b_hat)
-      bit_e, block_e = _count(b, b_hat)
+      bit_e, block_e = count_fn(b, b_hat)
       bit_n = b.numel()
       block_n = int(b.numel() / b.shape[-1])
       if dist is not None:                       # 4 x int64 all-reduce: identical stop decisions on all ranks

@@ -1,0 +1,252 @@
+"""GPU tests of the pieces either side of the decoders: AWGN front end (statistical parity: the
+reference draws from torch's CPU mt19937, the kernel from Philox), error counters, CRC-aided list
+decoding, the link model + Monte-Carlo loop (BER/BLER inside confidence intervals of the oracle),
+and the host-buffer C-ABI entry points."""
+import numpy as np
+import pytest
+
+from util import golden, golden_names, unpack_words, pack_words, awgn_logits
+
+pytestmark = pytest.mark.gpu
+
+
+def _env():
+    import torch
+    import d_kernels as dk
+    from oracle import polar_oracle as po, c_oracle as co
+    return torch, dk, po, co, torch.device("cuda", 0)
+
+
+@pytest.mark.parametrize("n,k", [(8, 4), (32, 16), (64, 32), (1024, 512), (4096, 2048)])
+def test_frontend_structure_and_statistics(n, k):
+    torch, dk, po, co, dev = _env()
+    fp = po.rm_frozen_pos(n, n - k)
+    tables = dk.code_tables(fp, n, dev)
+    B = max(4096, (1 << 21) // n)
+    ebno = 2.0
+    no = po.ebnodb2no(ebno, 2, k / n)
+    u, c, lg = dk.awgn_frontend(tables, B, no, seed=99, offset=5, want_codeword=True)
+    ub = unpack_words(u.cpu().numpy(), n)
+    cb = unpack_words(c.cpu().numpy(), n)
+    assert not ub[:, fp].any()                                         # frozen positions carry 0 (enc.py:33-35)
+    assert abs(ub[:, po.info_positions(fp, n)].mean() - 0.5) < 5 * 0.5 / np.sqrt(B * k)   # Bernoulli(1/2) source
+    assert np.array_equal(co.polar_transform(ub), cb)                  # codeword = u.G
+    y = lg.cpu().numpy().astype(np.float64) * (-no / (2 * np.sqrt(2)))   # invert the closed-form demapper
+    z = (y - (1 - 2.0 * cb) / np.sqrt(2)) / np.sqrt(no / 2)            # should be N(0,1)
+    N = z.size
+    assert abs(z.mean()) < 5 / np.sqrt(N)
+    assert abs(z.var() - 1) < 5 * np.sqrt(2 / N)
+    assert abs((z ** 4).mean() - 3) < 5 * np.sqrt(96 / N)
+    assert abs(np.mean(z[:, 0::2] * z[:, 1::2])) < 5 / np.sqrt(N / 2)  # real / imaginary parts uncorrelated
+    assert abs(np.mean(np.abs(z) > 3) - 0.0026998) < 5 * np.sqrt(0.0027 / N)
+    # counter-based stream: pure function of (seed, offset + b, i), independent of the launch geometry
+    u2, _, lg2 = dk.awgn_frontend(tables, B // 2, no, seed=99, offset=5 + B // 2)
+    assert torch.equal(lg2, lg[B // 2:]) and torch.equal(u2, u[B // 2:])
+    _, _, lg3 = dk.awgn_frontend(tables, 64, no, seed=100, offset=5)
+    assert not torch.equal(lg3, lg[:64])
+    # Mapper/AWGN/Demapper-only entry point reproduces the same noise for the same codewords
+    cf = torch.from_numpy(cb.astype(np.float32)).to(dev)
+    if n >= 4:
+        assert torch.equal(dk.qpsk_awgn_llr(cf, no, seed=99, offset=5), lg)
+
+
+def test_error_counters_match_numpy():
+    torch, dk, po, co, dev = _env()
+    rng = np.random.default_rng(3)
+    for (B, k) in ((1, 1), (1000, 32), (777, 512), (50, 1000)):
+        a = rng.integers(0, 2, size=(B, k)).astype(np.float32)
+        b = a.copy()
+        flip = rng.random((B, k)) < 0.01
+        b[flip] = 1 - b[flip]
+        cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+        dk.count_errors_f32(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev), cnt)
+        assert cnt.cpu().tolist() == [po.count_errors(a, b), po.count_block_errors(a, b)]
+    n = 256
+    a = rng.integers(0, 2, size=(999, n)).astype(np.uint8)
+    b = a ^ (rng.random((999, n)) < 0.003)
+    mask = rng.integers(0, 2, size=n).astype(np.uint8)
+    cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    to = lambda x: torch.from_numpy(pack_words(x).view(np.int32)).to(dev)
+    dk.count_errors_packed(to(a), to(b), to(mask[None])[0], n, cnt)
+    d = (a != b) & (mask[None] != 0)
+    assert cnt.cpu().tolist() == [int(d.sum()), int(d.any(1).sum())]
+    from my_sn.sim import count_errors, count_block_errors
+    x = torch.from_numpy(a[:, :7].astype(np.float32)).to(dev); y = torch.from_numpy(b[:, :7].astype(np.float32)).to(dev)
+    assert int(count_errors(x, y)) == int((a[:, :7] != b[:, :7]).sum())
+    assert int(count_block_errors(x, y)) == int((a[:, :7] != b[:, :7]).any(1).sum())
+
+
+def test_pack_unpack_roundtrip():
+    torch, dk, po, co, dev = _env()
+    rng = np.random.default_rng(4)
+    for n in (8, 32, 96, 1024):
+        x = rng.integers(0, 2, size=(257, n)).astype(np.float32)
+        p = dk.pack_bits(torch.from_numpy(x).to(dev))
+        assert np.array_equal(unpack_words(p.cpu().numpy(), n), x.astype(np.uint8))
+        pos = torch.arange(n, dtype=torch.int32, device=dev)
+        assert np.array_equal(dk.unpack_info(p, pos, n).cpu().numpy(), x)
+
+
+@pytest.mark.parametrize("name", golden_names("sclcrc_"))
+def test_crc_aided_scl_matches_composed_reference(name):
+    torch, dk, po, co, dev = _env()
+    from my_sn.fec.polar.dec import SCL_Dec
+    d = golden(name)
+    n = d["logits"].shape[1]
+    dec = SCL_Dec(d["frozen_pos"], n, list_size=8, crc_degree=str(d["crc_degree"]))
+    out = dec(torch.from_numpy(d["logits"]).to(dev)).cpu().numpy().astype(np.uint8)
+    rb = d["robust"]
+    assert np.array_equal(out[rb], d["u_sel"][rb])
+    assert dec.k_crc == po.CRC_COEFFS[str(d["crc_degree"])][0]
+
+
+def test_crc_aided_scl_matches_oracle_random_and_beats_plain_scl():
+    torch, dk, po, co, dev = _env()
+    from my_sn.fec.polar.dec import SCL_Dec
+    from polar.polar_scl import SCL_Dec as PlainSCL
+    n, k, L, deg = 128, 64, 8, "CRC11"
+    fp = np.asarray(golden("frozen_sets")["g5_128_64"])
+    rng = np.random.default_rng(11)
+    B = 3000
+    payload = rng.integers(0, 2, size=(B, k - 11)).astype(np.uint8)
+    bits = po.crc_encode(payload, deg)
+    c = po.encode(bits, fp, n)
+    no = po.ebnodb2no(2.0, 2, k / n)
+    y = (1 - 2.0 * c) / np.sqrt(2) + np.sqrt(no / 2) * rng.standard_normal((B, n))
+    logits = (-2 * np.sqrt(2) * y / no).astype(np.float32)
+    u_list, pm = co.scl_decode_full(logits, po.frozen_vec(fp, n), L)
+    sel, idx = po.scl_crc_select(u_list, pm, fp, n, deg)
+    u_b, pm_b = po.scl_decode_full(logits[:600], po.frozen_vec(fp, n), L, use_log1p=True)   # conditioning probe
+    sel_b, _ = po.scl_crc_select(u_b, pm_b, fp, n, deg)
+    x = torch.from_numpy(logits).to(dev)
+    got = SCL_Dec(fp, n, L, crc_degree=deg)(x).cpu().numpy()
+    diff = np.any(got != sel, axis=1)
+    probe = np.any(sel_b != sel[:600], axis=1)
+    # decisions agree everywhere except (at most) on ill-conditioned codewords, whose rate the two oracle variants bound
+    assert diff.mean() <= max(3 * probe.mean(), 2e-3), (diff.mean(), probe.mean())
+    assert not diff[:600][~probe].any() or diff.mean() < 2e-3
+    plain = PlainSCL(fp, n, L)(x).cpu().numpy()
+    bler_aided = np.any(got != bits, axis=1).mean()
+    bler_plain = np.any(plain != bits, axis=1).mean()
+    assert (idx != 0).sum() > 0 and bler_aided < bler_plain
+
+
+def test_link_model_and_sim_ber_inside_oracle_confidence_interval():
+    """README configuration (k=32, n=64) on the GPU: SC and SCL-8 BLER/BER curves vs the oracle on
+    independent noise, 6-sigma binomial bands (both estimates are Monte-Carlo)."""
+    torch, dk, po, co, dev = _env()
+    from polar.froze import get_Kern_frozen_bits
+    from polar.enc import PolarEncoder
+    from polar.polar_sc import SC_Dec
+    from polar.polar_scl import SCL_Dec
+    from z_sys_model.awgn_model import System_AWGN_model
+    from my_sn.plotting import PlotBER
+    from d_kernels import F2
+    n, k, bs = 64, 32, 40000
+    fp = golden("frozen_sets")["rm_64_32"]
+    ebnos = np.arange(0, 5, 1.0)
+    rng = np.random.default_rng(77)
+    for name, make, L in (("sc", lambda: SC_Dec(fp, n), 0), ("scl", lambda: SCL_Dec(fp, n, 8), 8)):
+        torch.manual_seed(42)
+        model = System_AWGN_model(n, k, PolarEncoder(fp, n, None), make())
+        plot = PlotBER("t")
+        ber, bler = plot.simulate(model, ebnos, batch_size=bs, max_mc_iter=1, add_bler=True, verbose=False, target_block_errs=10 ** 9)
+        assert len(plot.ber) == 2 and plot.legend[1].endswith("(BLER)")
+        for i, e in enumerate(ebnos):
+            u, logits = awgn_logits(rng, n, k, fp, bs, float(e))
+            if L == 0:
+                hat = co.sc_decode_full(logits, po.frozen_vec(fp, n))[:, po.info_positions(fp, n)]
+            else:
+                hat = co.scl_decode_full(logits, po.frozen_vec(fp, n), L)[0][:, 0][:, po.info_positions(fp, n)]
+            p_ref = np.any(hat != u, axis=1).mean()
+            p = float(bler[i])
+            band = 6 * np.sqrt(max(p_ref, 1e-4) * (1 - p_ref) / bs * 2) + 1e-4
+            assert abs(p - p_ref) < band, (name, e, p, p_ref)
+            b_ref = (hat != u).mean()
+            assert abs(float(ber[i]) - b_ref) < 6 * np.sqrt(max(b_ref, 1e-4) / bs * 2) + 1e-4, (name, e)
+    # README KAT curve (bs=100): the GPU curve must also be compatible with the published points
+    kat = golden("readme_kat")
+    torch.manual_seed(42)
+    model = System_AWGN_model(n, k, PolarEncoder(fp, n, None), SC_Dec(fp, n))
+    from my_sn.sim import sim_ber
+    ber, bler = sim_ber(model, kat["ebno_dbs"], 20000, 1, verbose=False, early_stop=False)
+    for p_pub, p in zip(kat["sc_bler"], bler.numpy()):
+        assert abs(p_pub - p) < 5 * np.sqrt(max(p, 1e-3) * (1 - p) / 100) + 0.02
+    # layer-by-layer composition (fused=False) gives the same statistics
+    m2 = System_AWGN_model(n, k, PolarEncoder(fp, n, None), SC_Dec(fp, n), fused=False)
+    b, bh = m2(20000, 2.0)
+    p2 = float((b != bh).any(-1).float().mean())
+    assert abs(p2 - float(bler[4])) < 6 * np.sqrt(p2 * (1 - p2) / 20000 * 2)
+    c, _ = System_AWGN_model(n, k, PolarEncoder(fp, n, None), SC_Dec(fp, n), cw_estimates=True)(16, 2.0)
+    assert c.shape == (16, n)
+
+
+def test_my_sn_encoder_and_parity_check():
+    torch, dk, po, co, dev = _env()
+    from my_sn.fec.polar.enc import PolarEncoder
+    fp = golden("frozen_sets")["rm_256_128"]
+    enc = PolarEncoder(fp, 256)
+    u = torch.randint(0, 2, (300, 128), device=dev, dtype=torch.float32)
+    c = enc(u)
+    assert np.array_equal(c.cpu().numpy().astype(np.uint8), po.encode(u.cpu().numpy(), fp, 256))
+    assert enc.check_parity(c)
+    c[3, 17] = 1 - c[3, 17]
+    assert not enc.check_parity(c)
+    with pytest.raises(AssertionError):
+        enc(torch.zeros(2, 100, device=dev))
+
+
+@pytest.mark.parametrize("n,B,chunk_mb", [(1024, 5000, 1), (64, 100000, 1), (2048, 700, 128)])
+def test_host_buffer_entry_points_match_device_path(n, B, chunk_mb, monkeypatch):
+    torch, dk, po, co, dev = _env()
+    monkeypatch.setenv("POLAR_HOST_CHUNK_MB", str(chunk_mb))     # several chunks -> exercises the 2-stream pipeline
+    k = n // 2
+    fp = po.rm_frozen_pos(n, n - k)
+    tables = dk.code_tables(fp, n, dev)
+    _, logits = awgn_logits(np.random.default_rng(n), n, k, fp, B, 3.0)
+    _, want = dk.sc_decode(torch.from_numpy(logits).to(dev), tables, want_info=False, want_packed=True)
+    h_in = torch.from_numpy(logits).pin_memory()
+    h_out = torch.empty((B, dk.words(n)), dtype=torch.int32).pin_memory()
+    dk.check(dk.lib().polar_sc_decode_host(h_in.data_ptr(), tables.mask_np.ctypes.data, n, B, h_out.data_ptr(), 0))
+    assert torch.equal(h_out, want.cpu())
+    Bs = min(B, 600)
+    res = dk.scl_decode(torch.from_numpy(logits[:Bs]).to(dev), tables, 4, want_packed=True, want_pm=True, want_info=False)
+    h_best = torch.empty((Bs, dk.words(n)), dtype=torch.int32)
+    h_pm = torch.empty((Bs, 4), dtype=torch.float64)
+    pageable = torch.from_numpy(logits[:Bs].copy())              # pageable memory must work too
+    dk.check(dk.lib().polar_scl_decode_host(pageable.data_ptr(), tables.mask_np.ctypes.data, n, 4, Bs, h_best.data_ptr(),
+                                            h_pm.data_ptr(), None, 0, 0))
+    assert torch.equal(h_best, res["u_packed"].cpu()) and torch.equal(h_pm, res["pm"].cpu())
+
+
+def test_full_size_properties_sc():
+    """BASELINE configs[1] size (n=1024, k=512, 2^20 codewords): size-independent properties.
+    (a) noiseless codewords decode to the transmitted bits; (b) decisions do not depend on how the batch is
+    split across launches; (c) the kernel is deterministic; (d) BLER sits in the oracle's confidence band."""
+    torch, dk, po, co, dev = _env()
+    n, k, B = 1024, 512, 1 << 20
+    fp = golden("frozen_sets")["rm_1024_512"]
+    tables = dk.code_tables(fp, n, dev)
+    no = po.ebnodb2no(4.0, 2, k / n)
+    u, c, lg = dk.awgn_frontend(tables, B, no, seed=5, want_codeword=True)
+    _, hat = dk.sc_decode(lg, tables, want_info=False, want_packed=True)
+    _, hat2 = dk.sc_decode(lg, tables, want_info=False, want_packed=True)
+    assert torch.equal(hat, hat2)
+    parts = torch.cat([dk.sc_decode(lg[a:b], tables, want_info=False, want_packed=True)[1]
+                       for a, b in ((0, 7), (7, 100003), (100003, B))])
+    assert torch.equal(parts, hat)
+    cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    dk.count_errors_packed(u, hat, tables.info_mask, n, cnt)
+    bler = cnt[1].item() / B
+    ref_u, ref_lg = awgn_logits(np.random.default_rng(8), n, k, fp, 20000, 4.0)
+    ref_hat = co.sc_decode_full(ref_lg, po.frozen_vec(fp, n))[:, po.info_positions(fp, n)]
+    p_ref = np.any(ref_hat != ref_u, axis=1).mean()
+    assert abs(bler - p_ref) < 6 * np.sqrt(p_ref * (1 - p_ref) / 20000)
+    # noiseless: logits = -/+ big for bit 0/1
+    cb = unpack_words(c[:4096].cpu().numpy(), n).astype(np.float32)
+    clean = torch.from_numpy((2 * cb - 1) * 8.0).to(dev)
+    _, h3 = dk.sc_decode(clean, tables, want_info=False, want_packed=True)
+    assert torch.equal(h3, u[:4096])
+    # bit-exact vs the oracle on a slice of the full-size batch
+    sl = slice(B - 3000, B)
+    assert np.array_equal(unpack_words(hat[sl].cpu().numpy(), n), co.sc_decode_full(lg[sl].cpu().numpy(), po.frozen_vec(fp, n)))

@@ -53,6 +53,7 @@ def test_sc_all_codewords_per_warp_variants(cw, monkeypatch):
     from oracle import polar_oracle as po, c_oracle as co
     dk = _dk()
     n, k, B = 256, 128, 1111
+    monkeypatch.setenv("POLAR_SC_MODE", "0")           # warp-per-CW-codewords mapping
     monkeypatch.setenv("POLAR_SC_CW", str(cw))
     fp = po.rm_frozen_pos(n, n - k)
     _, logits = awgn_logits(np.random.default_rng(cw), n, k, fp, B, 2.0)
@@ -60,6 +61,25 @@ def test_sc_all_codewords_per_warp_variants(cw, monkeypatch):
     tables = dk.code_tables(fp, n, torch.device("cuda", 0))
     _, u_packed = dk.sc_decode(torch.from_numpy(logits).cuda(), tables, want_info=False, want_packed=True)
     assert np.array_equal(unpack_words(u_packed.cpu().numpy(), n), ref)
+
+
+@pytest.mark.parametrize("ctas,threads,n", [(1, 32, 256), (2, 128, 1024), (3, 64, 512), (4, 256, 1024), (8, 128, 2048), (16, 96, 64)])
+def test_sc_cta_mapping_variants(ctas, threads, n, monkeypatch):
+    import torch
+    from oracle import polar_oracle as po, c_oracle as co
+    dk = _dk()
+    k, B = n // 2, 3001
+    monkeypatch.setenv("POLAR_SC_MODE", "1")           # CTA-cooperative mapping (default)
+    monkeypatch.setenv("POLAR_SC_CTAS", str(ctas))
+    monkeypatch.setenv("POLAR_SC_THREADS", str(threads))
+    fp = po.rm_frozen_pos(n, n - k)
+    _, logits = awgn_logits(np.random.default_rng(ctas), n, k, fp, B, 3.0)
+    logits[::9] = np.round(logits[::9])
+    ref = co.sc_decode_full(logits, po.frozen_vec(fp, n))
+    tables = dk.code_tables(fp, n, torch.device("cuda", 0))
+    u_info, u_packed = dk.sc_decode(torch.from_numpy(logits).cuda(), tables, want_info=True, want_packed=True)
+    assert np.array_equal(unpack_words(u_packed.cpu().numpy(), n), ref)
+    assert np.array_equal(u_info.cpu().numpy().astype(np.uint8), ref[:, po.info_positions(fp, n)])
 
 
 def test_sc_extreme_frozen_patterns():
