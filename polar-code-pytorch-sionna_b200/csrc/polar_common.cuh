@@ -68,6 +68,8 @@ PHD uint32_t ptransform(uint32_t x) {
 //  rate-0 (all frozen): u = beta = 0.
 //  rate-1 (none frozen): beta = hard decisions of x, u = T(beta) -- identical to the recursion
 //   unless some x is exactly 0 (reference tie rule llr==0 -> 1), which falls through.
+//  left child rate-0: its f values are never used; the right child's LLRs are g(a,b,0) = a + b
+//   (a REP node -- all frozen but the last leaf -- thus reduces to the reference's own add tree).
 template <int T, bool CLIPPED = false>
 struct SubTree {
   static constexpr int N = 1 << T, H = N / 2;
@@ -76,19 +78,25 @@ struct SubTree {
   PHD static uint32_t run(const float (&x)[N], uint32_t fm, uint32_t &u) {
     fm &= FULL;
     if (fm == FULL) { u = 0; return 0; }
-    if (T >= 3 && fm == 0) {
+    if (fm == 0) {
       uint32_t hd = 0; bool zero = false;
 #pragma unroll
-      for (int j = 0; j < N; ++j) { hd |= (uint32_t)(x[j] < 0.0f) << j; zero |= (x[j] == 0.0f); }
+      for (int j = 0; j < N; ++j) { hd |= (f2u(x[j]) >> 31) << j; zero |= (x[j] == 0.0f); }
       if (!zero) { u = ptransform<T>(hd); return hd; }
     }
     float y[H];
+    uint32_t ul = 0, ur, bl = 0;
+    if ((fm & HALF) != HALF) {
 #pragma unroll
-    for (int j = 0; j < H; ++j) y[j] = CLIPPED ? f_minsum_noclip(x[j], x[j + H]) : f_minsum(x[j], x[j + H]);
-    uint32_t ul, ur;
-    uint32_t bl = SubTree<T - 1, true>::run(y, fm & HALF, ul);
+      for (int j = 0; j < H; ++j) y[j] = CLIPPED ? f_minsum_noclip(x[j], x[j + H]) : f_minsum(x[j], x[j + H]);
+      bl = SubTree<T - 1, true>::run(y, fm & HALF, ul);
 #pragma unroll
-    for (int j = 0; j < H; ++j) y[j] = g_minsum(x[j], x[j + H], (bl << (31 - j)) & 0x80000000u);
+      for (int j = 0; j < H; ++j) y[j] = g_minsum(x[j], x[j + H], (bl << (31 - j)) & 0x80000000u);
+    } else {
+      // left child is rate-0: its decisions and partial sums are 0, so g = (1-0).a + b
+#pragma unroll
+      for (int j = 0; j < H; ++j) y[j] = x[j] + x[j + H];
+    }
     uint32_t br = SubTree<T - 1, false>::run(y, fm >> H, ur);
     u = ul | (ur << H);
     return (bl ^ br) | (br << H);
@@ -100,6 +108,128 @@ struct SubTree<0, CLIPPED> {
     // polar_sc.py:90-98: frozen -> 0; else u = [llr <= 0] (exact 0 -> 1)
     uint32_t bit = ((fm & 1u) == 0u && x[0] <= 0.0f) ? 1u : 0u;
     u = bit; return bit;
+  }
+};
+
+
+// Rate-1 node: beta = hard decisions (sign bits) of x, u = T(beta).  Exact unless some x is exactly 0
+// (returns false then; the caller falls back to the recursion).  Balanced trees instead of chains: the
+// caller is a single lane on the latency-critical path.
+template <int T>
+PDEV bool rate1_decide(const float (&x)[1 << T], uint32_t &beta, uint32_t &u) {
+  constexpr int N = 1 << T, G = N < 8 ? N : 8;   // groups of 8 bound the number of live temporaries
+  uint32_t hd = 0;
+  float mn = 1.0f;
+#pragma unroll
+  for (int g0 = 0; g0 < N; g0 += G) {
+    uint32_t t[G];
+    float a[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) { t[j] = (f2u(x[g0 + j]) >> 31) << (g0 + j); a[j] = fabsf(x[g0 + j]); }
+#pragma unroll
+    for (int st = G / 2; st >= 1; st >>= 1) {
+#pragma unroll
+      for (int j = 0; j < st; ++j) { t[j] |= t[j + st]; a[j] = fminf(a[j], a[j + st]); }
+    }
+    hd |= t[0]; mn = fminf(mn, a[0]);
+  }
+  beta = hd; u = ptransform<T>(hd);
+  return mn != 0.0f;
+}
+
+// Same contract as SubTree<T>::run, but every level T >= 3 is a ROLLED two-iteration loop over its
+// children (h = 0: f then left child, h = 1: g then right child) with the child inlined once.  Stage s
+// of the subtree always lives in the same registers (one live node per stage), so indices stay
+// compile-time while the code is ~0.5 K instructions instead of ~2 K for the fully unrolled recursion --
+// small enough to stay in the instruction cache when several CTAs run different phases on one SM.
+template <int T>
+struct RollTree {
+  static constexpr int N = 1 << T, H = N / 2;
+  static constexpr uint32_t FULL = (N == 32) ? 0xFFFFFFFFu : ((1u << N) - 1u);
+  static constexpr uint32_t HALF = (1u << H) - 1u;
+  PDEV static uint32_t run(const float (&x)[N], uint32_t fm, uint32_t &u) {
+    fm &= FULL;
+    if (fm == FULL) { u = 0; return 0; }
+    if (fm == 0) {
+      uint32_t b;
+      if (rate1_decide<T>(x, b, u)) return b;
+    }
+    float y[H];
+    uint32_t bl = 0, ul = 0, bc = 0, uc = 0;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t fmc = (h == 0) ? (fm & HALF) : (fm >> H);
+      if (fmc == HALF) { bc = 0; uc = 0; continue; }      // rate-0 child: decisions and partial sums are 0
+      if (h == 0) {
+#pragma unroll
+        for (int j = 0; j < H; ++j) y[j] = f_minsum(x[j], x[j + H]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < H; ++j) y[j] = g_minsum(x[j], x[j + H], (bl << (31 - j)) & 0x80000000u);
+      }
+      bc = RollTree<T - 1>::run(y, fmc, uc);
+      if (h == 0) { bl = bc; ul = uc; }
+    }
+    u = ul | (uc << H);
+    return (bl ^ bc) | (bc << H);
+  }
+};
+// 4-leaf subtree, branch-free.  g is evaluated speculatively: a+b (u=0) and b-a (u=1) are formed while the
+// decision they depend on is still in flight, then selected -- (1-2u).a + b is exactly one of the two
+// (polar_sc.py:49-53), so this is bit-identical while the dependent chain per leaf drops from
+// ~7 to ~3 instructions.  Frozen leaves are forced to 0 through the (warp-uniform) mask bits.
+PDEV uint32_t leaf4(const float (&x)[4], uint32_t fm, uint32_t &u) {
+  const bool n0 = !(fm & 1u), n1 = !(fm & 2u), n2 = !(fm & 4u), n3 = !(fm & 8u);
+  const float a0 = f_minsum(x[0], x[2]), a1 = f_minsum(x[1], x[3]);
+  const float s0 = x[0] + x[2], d0 = x[2] - x[0], s1 = x[1] + x[3], d1 = x[3] - x[1];
+  const float l0 = f_minsum_noclip(a0, a1);
+  const float sa = a0 + a1, da = a1 - a0;
+  const bool u0 = n0 & (l0 <= 0.0f);
+  const float l1 = u0 ? da : sa;
+  const bool u1 = n1 & (l1 <= 0.0f);
+  const bool p0 = u0 != u1;                      // partial sums of the left pair: (u0^u1, u1)
+  const float b0 = p0 ? d0 : s0, b1 = u1 ? d1 : s1;
+  const float l2 = f_minsum(b0, b1);
+  const float sb = b0 + b1, db = b1 - b0;
+  const bool u2 = n2 & (l2 <= 0.0f);
+  const float l3 = u2 ? db : sb;
+  const bool u3 = n3 & (l3 <= 0.0f);
+  const bool p2 = u2 != u3;
+  u = (uint32_t)u0 | ((uint32_t)u1 << 1) | ((uint32_t)u2 << 2) | ((uint32_t)u3 << 3);
+  return (uint32_t)(p0 != p2) | ((uint32_t)(u1 != u3) << 1) | ((uint32_t)p2 << 2) | ((uint32_t)u3 << 3);
+}
+template <>
+struct RollTree<2> {
+  PDEV static uint32_t run(const float (&x)[4], uint32_t fm, uint32_t &u) {
+    fm &= 0xFu;
+    if (fm == 0xFu) { u = 0; return 0; }
+    return leaf4(x, fm, u);
+  }
+};
+// 8-leaf subtree: two leaf4 with the same speculative g between them.
+template <>
+struct RollTree<3> {
+  PDEV static uint32_t run(const float (&x)[8], uint32_t fm, uint32_t &u) {
+    fm &= 0xFFu;
+    if (fm == 0xFFu) { u = 0; return 0; }
+    if (fm == 0) {
+      uint32_t b;
+      if (rate1_decide<3>(x, b, u)) return b;
+    }
+    float y[4], sd[4], df[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { sd[j] = x[j] + x[j + 4]; df[j] = x[j + 4] - x[j]; }
+    uint32_t bl = 0, ul = 0, br, ur;
+    if ((fm & 0xFu) != 0xFu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y[j] = f_minsum(x[j], x[j + 4]);
+      bl = leaf4(y, fm & 0xFu, ul);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = ((bl >> j) & 1u) ? df[j] : sd[j];
+    br = RollTree<2>::run(y, fm >> 4, ur);
+    u = ul | (ur << 4);
+    return (bl ^ br) | (br << 4);
   }
 };
 

@@ -82,6 +82,52 @@ def test_sc_cta_mapping_variants(ctas, threads, n, monkeypatch):
     assert np.array_equal(u_info.cpu().numpy().astype(np.uint8), ref[:, po.info_positions(fp, n)])
 
 
+@pytest.mark.parametrize("cw,threads,ctas,n", [(32, 256, 0, 128), (32, 128, 0, 256), (7, 256, 2, 512), (32, 256, 0, 1024),
+                                               (26, 128, 4, 1024), (1, 256, 1, 1024), (32, 256, 0, 2048),
+                                               (16, 128, 0, 4096), (32, 256, 0, 8192)])
+def test_sc3_mapping_variants(cw, threads, ctas, n, monkeypatch):
+    """polar_sc3.cu (default mapping): virtual top stage for n >= 1024, 64-leaf register subtrees."""
+    import torch
+    from oracle import polar_oracle as po, c_oracle as co
+    dk = _dk()
+    k, B = n // 2, 2000 if n <= 2048 else 300
+    monkeypatch.setenv("POLAR_SC_MODE", "2")
+    monkeypatch.setenv("POLAR_SC_CTA_CW", str(cw))
+    monkeypatch.setenv("POLAR_SC_CTAS", str(ctas))
+    monkeypatch.setenv("POLAR_SC_THREADS", str(threads))
+    fp = po.rm_frozen_pos(n, n - k)
+    _, logits = awgn_logits(np.random.default_rng(cw + n), n, k, fp, B, 3.0)
+    logits[::9] = np.round(logits[::9])
+    ref = co.sc_decode_full(logits, po.frozen_vec(fp, n))
+    tables = dk.code_tables(fp, n, torch.device("cuda", 0))
+    u_info, u_packed = dk.sc_decode(torch.from_numpy(logits).cuda(), tables, want_info=True, want_packed=True)
+    assert np.array_equal(unpack_words(u_packed.cpu().numpy(), n), ref)
+    assert np.array_equal(u_info.cpu().numpy().astype(np.uint8), ref[:, po.info_positions(fp, n)])
+
+
+@pytest.mark.parametrize("n", [128, 1024, 2048])
+def test_sc3_extreme_frozen_patterns(n, monkeypatch):
+    """rate-0 halves / quarters (virtual-stage corner cases), none frozen, single info bit, alternating, 5G-like."""
+    import torch
+    from oracle import polar_oracle as po, c_oracle as co
+    dk = _dk()
+    monkeypatch.setenv("POLAR_SC_MODE", "2")
+    B = 333
+    rng = np.random.default_rng(n)
+    logits = (rng.standard_normal((B, n)) * 4).astype(np.float32)
+    logits[::5] = np.round(logits[::5])
+    pats = [np.arange(n), np.arange(0), np.arange(n - 1), np.arange(0, n, 2), np.arange(n // 2), np.arange(n // 2, n),
+            np.arange(n // 4), np.arange(3 * n // 4), np.concatenate([np.arange(n // 4), np.arange(n // 2, 3 * n // 4)]),
+            np.concatenate([np.arange(64), np.arange(128, 128 + 64)]) % n, np.arange(n // 4, n),
+            np.sort(rng.choice(n, n // 3, replace=False))]
+    for fp in pats:
+        fp = np.unique(fp)
+        ref = co.sc_decode_full(logits, po.frozen_vec(fp, n))
+        tables = dk.code_tables(fp, n, torch.device("cuda", 0))
+        _, u_packed = dk.sc_decode(torch.from_numpy(logits).cuda(), tables, want_info=False, want_packed=True)
+        assert np.array_equal(unpack_words(u_packed.cpu().numpy(), n), ref), len(fp)
+
+
 def test_sc_extreme_frozen_patterns():
     """all-frozen, none-frozen, single info bit, alternating: exercises rate-0 / rate-1 shortcuts."""
     import torch

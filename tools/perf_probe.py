@@ -47,6 +47,20 @@ def main():
                 best, med = timeit(f)
                 print("SC-CTA n=%d B=%d ctas/SM=%d threads=%3d: %8.3f ms  %.3e cw/s  %.1f Gbit/s info  HBM-frac %.3f" %
                       (n, B, ctas, thr, best, B / best * 1e3, B / best * 1e3 * k / 1e9, B / best * 1e3 * (4 * n + k / 8) / 6552.3e9), flush=True)
+    elif what == "sc3":
+        B = int(sys.argv[3]) if len(sys.argv) > 3 else (1 << 28) // n
+        _, _, x = dk.awgn_frontend(tables, B, no, 1234)
+        up = torch.empty((B, dk.words(n)), dtype=torch.int32, device=dev)
+        os.environ["POLAR_SC_MODE"] = "2"
+        for cw in [int(v) for v in os.environ.get("CWS", "32").split(",")]:
+            for ctas in [int(v) for v in os.environ.get("CTAS", "0,2,3,4").split(",")]:
+                for thr in [int(v) for v in os.environ.get("THREADS", "128,256").split(",")]:
+                    os.environ["POLAR_SC_CTAS"] = str(ctas); os.environ["POLAR_SC_THREADS"] = str(thr)
+                    os.environ["POLAR_SC_CTA_CW"] = str(cw)
+                    f = lambda: dk.check(dk.lib().polar_sc_decode_f32(dk.ptr(x), dk.ptr(tables.frozen_mask), n, B, dk.ptr(up), None, None, 0, dk.stream_ptr(dev)))
+                    best, med = timeit(f)
+                    print("SC3 n=%d B=%d cw=%d ctas/SM=%d threads=%3d bwdiv=%s: %8.3f ms  %.3e cw/s  %.1f Gbit/s info  HBM-frac %.3f" %
+                          (n, B, cw, ctas, thr, os.environ.get("POLAR_SC3_BWDIV", "sms"), best, B / best * 1e3, B / best * 1e3 * k / 1e9, B / best * 1e3 * (4 * n + k / 8) / 6552.3e9), flush=True)
     elif what == "sc":
         os.environ["POLAR_SC_MODE"] = "0"
         B = int(sys.argv[3]) if len(sys.argv) > 3 else (1 << 28) // n
