@@ -206,29 +206,96 @@ struct RollTree<2> {
     return leaf4(x, fm, u);
   }
 };
-// 8-leaf subtree: two leaf4 with the same speculative g between them.
+// 8-leaf subtree: two leaf4 with the same speculative g between them; branch-free apart from the rate-0 skip
+// (the uniform tests cost more on this serial path than the arithmetic they would save).
 template <>
 struct RollTree<3> {
   PDEV static uint32_t run(const float (&x)[8], uint32_t fm, uint32_t &u) {
     fm &= 0xFFu;
     if (fm == 0xFFu) { u = 0; return 0; }
-    if (fm == 0) {
-      uint32_t b;
-      if (rate1_decide<3>(x, b, u)) return b;
-    }
     float y[4], sd[4], df[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { sd[j] = x[j] + x[j + 4]; df[j] = x[j + 4] - x[j]; }
-    uint32_t bl = 0, ul = 0, br, ur;
-    if ((fm & 0xFu) != 0xFu) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) y[j] = f_minsum(x[j], x[j + 4]);
-      bl = leaf4(y, fm & 0xFu, ul);
-    }
+    for (int j = 0; j < 4; ++j) { y[j] = f_minsum(x[j], x[j + 4]); sd[j] = x[j] + x[j + 4]; df[j] = x[j + 4] - x[j]; }
+    uint32_t ul, ur;
+    const uint32_t bl = leaf4(y, fm & 0xFu, ul);
 #pragma unroll
     for (int j = 0; j < 4; ++j) y[j] = ((bl >> j) & 1u) ? df[j] : sd[j];
-    br = RollTree<2>::run(y, fm >> 4, ur);
+    const uint32_t br = leaf4(y, fm >> 4, ur);
     u = ul | (ur << 4);
+    return (bl ^ br) | (br << 4);
+  }
+};
+
+// ---- partial-sum-only subtrees (polar_sc3.cu) -------------------------------------------------------
+// The decisions of a node are the polar transform of its partial sums (u = T(beta), T an involution), so
+// the serial per-lane path only has to produce beta; u is recovered once per codeword at the end.
+PDEV uint32_t leaf4_beta(const float (&x)[4], uint32_t fm) {
+  const bool n0 = !(fm & 1u), n1 = !(fm & 2u), n2 = !(fm & 4u), n3 = !(fm & 8u);
+  const float a0 = f_minsum(x[0], x[2]), a1 = f_minsum(x[1], x[3]);
+  const float s0 = x[0] + x[2], d0 = x[2] - x[0], s1 = x[1] + x[3], d1 = x[3] - x[1];
+  const float l0 = f_minsum_noclip(a0, a1);
+  const float sa = a0 + a1, da = a1 - a0;
+  const bool u0 = n0 & (l0 <= 0.0f);
+  const float l1 = u0 ? da : sa;
+  const bool u1 = n1 & (l1 <= 0.0f);
+  const bool p0 = u0 != u1;                      // partial sums of the left pair: (u0^u1, u1)
+  const float b0 = p0 ? d0 : s0, b1 = u1 ? d1 : s1;
+  const float l2 = f_minsum(b0, b1);
+  const float sb = b0 + b1, db = b1 - b0;
+  const bool u2 = n2 & (l2 <= 0.0f);
+  const float l3 = u2 ? db : sb;
+  const bool u3 = n3 & (l3 <= 0.0f);
+  const bool p2 = u2 != u3;
+  return (uint32_t)(p0 != p2) | ((uint32_t)(u1 != u3) << 1) | ((uint32_t)p2 << 2) | ((uint32_t)u3 << 3);
+}
+template <int T>
+PDEV bool rate1_beta(const float (&x)[1 << T], uint32_t &beta) {
+  uint32_t u;
+  return rate1_decide<T>(x, beta, u);      // the transform of u is dead code here and is removed
+}
+template <int T>
+struct BetaTree {   // rolled two-iteration loop per level, like RollTree
+  static constexpr int N = 1 << T, H = N / 2;
+  static constexpr uint32_t FULL = (N == 32) ? 0xFFFFFFFFu : ((1u << N) - 1u);
+  static constexpr uint32_t HALF = (1u << H) - 1u;
+  PDEV static uint32_t run(const float (&x)[N], uint32_t fm) {
+    fm &= FULL;
+    if (fm == FULL) return 0;
+    if (fm == 0) {
+      uint32_t b;
+      if (rate1_beta<T>(x, b)) return b;
+    }
+    float y[H];
+    uint32_t bl = 0, bc = 0;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t fmc = (h == 0) ? (fm & HALF) : (fm >> H);
+      if (fmc == HALF) { bc = 0; continue; }
+      if (h == 0) {
+#pragma unroll
+        for (int j = 0; j < H; ++j) y[j] = f_minsum(x[j], x[j + H]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < H; ++j) y[j] = g_minsum(x[j], x[j + H], (bl << (31 - j)) & 0x80000000u);
+      }
+      bc = BetaTree<T - 1>::run(y, fmc);
+      if (h == 0) bl = bc;
+    }
+    return (bl ^ bc) | (bc << H);
+  }
+};
+template <>
+struct BetaTree<3> {
+  PDEV static uint32_t run(const float (&x)[8], uint32_t fm) {
+    fm &= 0xFFu;
+    if (fm == 0xFFu) return 0;
+    float y[4], sd[4], df[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { y[j] = f_minsum(x[j], x[j + 4]); sd[j] = x[j] + x[j + 4]; df[j] = x[j + 4] - x[j]; }
+    const uint32_t bl = leaf4_beta(y, fm & 0xFu);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = ((bl >> j) & 1u) ? df[j] : sd[j];
+    const uint32_t br = leaf4_beta(y, fm >> 4);
     return (bl ^ br) | (br << 4);
   }
 };

@@ -18,7 +18,7 @@ int device_max_smem_optin();
 
 // polar_sc3.cu: SC decoder with compile-time tree geometry (n in [128, 8192])
 int launch_sc3(const float *logit, const uint32_t *fmask, int n, int64_t B, uint32_t *u_packed, float *u_info,
-               const int32_t *info_pos, int k, int cw, int threads, int ctas, cudaStream_t st);
+               const int32_t *info_pos, int k, int cw, int ctas, cudaStream_t st);
 
 inline bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
 

@@ -491,7 +491,7 @@ extern "C" int polar_sc_decode_f32(const float *d_logit, const uint32_t *d_froze
   const int mode = env_int("POLAR_SC_MODE", 2);
   if (mode == 2 && n >= 128)   // default: compile-time tree, virtual top stage, 64-leaf register subtrees (polar_sc3.cu)
     return launch_sc3(d_logit, d_frozen_mask, n, B, d_u_packed, d_u_info_f32, d_info_pos, k, env_int("POLAR_SC_CTA_CW", 32),
-                      env_int("POLAR_SC_THREADS", 256), env_int("POLAR_SC_CTAS", 0), st);
+                      env_int("POLAR_SC_CTAS", 0), st);
   if (mode >= 1) {
     // CTA mapping (default): up to 32 codewords per CTA, `ctas` CTAs per SM
     int ctas = env_int("POLAR_SC_CTAS", 3);

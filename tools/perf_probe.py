@@ -54,11 +54,18 @@ def main():
         os.environ["POLAR_SC_MODE"] = "2"
         for cw in [int(v) for v in os.environ.get("CWS", "32").split(",")]:
             for ctas in [int(v) for v in os.environ.get("CTAS", "0,2,3,4").split(",")]:
-                for thr in [int(v) for v in os.environ.get("THREADS", "128,256").split(",")]:
+                for thr in [128]:
                     os.environ["POLAR_SC_CTAS"] = str(ctas); os.environ["POLAR_SC_THREADS"] = str(thr)
                     os.environ["POLAR_SC_CTA_CW"] = str(cw)
                     f = lambda: dk.check(dk.lib().polar_sc_decode_f32(dk.ptr(x), dk.ptr(tables.frozen_mask), n, B, dk.ptr(up), None, None, 0, dk.stream_ptr(dev)))
                     best, med = timeit(f)
+                    if os.environ.get("POLAR_SC3_DBG") == "1":
+                        import ctypes
+                        L = ctypes.CDLL(dk.LIB_PATH); buf = (ctypes.c_ulonglong * 8)()
+                        L.polar_sc3_debug_read(buf); f(); torch.cuda.synchronize(); L.polar_sc3_debug_read(buf)
+                        v = list(buf); nb = max(v[7], 1)
+                        print("  CTA0 cycles/batch: virt %d  g %d  f %d  bottom %d  merge %d  out %d  | total %d  batches %d" %
+                              tuple([x // nb for x in v[:7]] + [v[7]]))
                     print("SC3 n=%d B=%d cw=%d ctas/SM=%d threads=%3d bwdiv=%s: %8.3f ms  %.3e cw/s  %.1f Gbit/s info  HBM-frac %.3f" %
                           (n, B, cw, ctas, thr, os.environ.get("POLAR_SC3_BWDIV", "sms"), best, B / best * 1e3, B / best * 1e3 * k / 1e9, B / best * 1e3 * (4 * n + k / 8) / 6552.3e9), flush=True)
     elif what == "sc":
