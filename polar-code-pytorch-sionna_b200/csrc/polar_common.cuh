@@ -35,15 +35,26 @@ PHD float u2f(uint32_t u) {
 // |clip(x)| = min(|x|,30), so the magnitude is min(|a|,|b|,30); the sign is the xor of the sign
 // bits.  When an input is +-0 the reference yields +-0 (sign(0)=0); so does this (sign of a zero
 // LLR is never observable: the leaf rule is llr<=0 -> 1 and g adds it).
+// The sign is taken from the product a*b (IEEE: sign(a*b) = sign(a) xor sign(b), also for zero, underflowed
+// and infinite products): FMUL issues on the FMA pipe, which this integer-heavy decoder leaves idle, instead
+// of a third ALU-pipe instruction.  (inf*0 = NaN only arises with magnitude 0, where the sign is unobservable.)
 PHD float f_minsum(float a, float b) {
   float mag = fminf(fminf(fabsf(a), fabsf(b)), kLlrMax);
+#if defined(__CUDA_ARCH__)
+  uint32_t sgn = f2u(__fmul_rn(a, b)) & 0x80000000u;
+#else
   uint32_t sgn = (f2u(a) ^ f2u(b)) & 0x80000000u;
+#endif
   return u2f(f2u(mag) | sgn);
 }
 // same, for inputs already known to lie in [-30, 30] (outputs of f): the clip is the identity.
 PHD float f_minsum_noclip(float a, float b) {
   float mag = fminf(fabsf(a), fabsf(b));
+#if defined(__CUDA_ARCH__)
+  uint32_t sgn = f2u(__fmul_rn(a, b)) & 0x80000000u;
+#else
   uint32_t sgn = (f2u(a) ^ f2u(b)) & 0x80000000u;
+#endif
   return u2f(f2u(mag) | sgn);
 }
 // g: (1-2u).a + b, unclipped, one rounding (polar_sc.py:49-53).  signmask = u ? 0x80000000 : 0.

@@ -20,6 +20,10 @@ int device_max_smem_optin();
 int launch_sc3(const float *logit, const uint32_t *fmask, int n, int64_t B, uint32_t *u_packed, float *u_info,
                const int32_t *info_pos, int k, int cw, int ctas, cudaStream_t st);
 
+// polar_sc4.cu: warp-autonomous SC decoder (n in [128, 2048])
+int launch_sc4(const float *logit, const uint32_t *fmask, int n, int64_t B, uint32_t *u_packed, float *u_info,
+               const int32_t *info_pos, int k, int warps, cudaStream_t st);
+
 inline bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
 
 #define POLAR_CHECK_LAUNCH(what)                                                           \

@@ -488,8 +488,10 @@ extern "C" int polar_sc_decode_f32(const float *d_logit, const uint32_t *d_froze
       default: return launch_small<5>(d_logit, d_frozen_mask, B, d_u_packed, d_u_info_f32, d_info_pos, k, st);
     }
   }
-  const int mode = env_int("POLAR_SC_MODE", 2);
-  if (mode == 2 && n >= 128)   // default: compile-time tree, virtual top stage, 64-leaf register subtrees (polar_sc3.cu)
+  const int mode = env_int("POLAR_SC_MODE", 3);
+  if (mode == 3 && n >= 128 && n <= 2048)   // default: warp-autonomous decoder, tensor memory scratch (polar_sc4.cu)
+    return launch_sc4(d_logit, d_frozen_mask, n, B, d_u_packed, d_u_info_f32, d_info_pos, k, env_int("POLAR_SC_WARPS_SM", 0), st);
+  if (mode >= 2 && n >= 128)   // default: compile-time tree, virtual top stage, 64-leaf register subtrees (polar_sc3.cu)
     return launch_sc3(d_logit, d_frozen_mask, n, B, d_u_packed, d_u_info_f32, d_info_pos, k, env_int("POLAR_SC_CTA_CW", 32),
                       env_int("POLAR_SC_CTAS", 0), st);
   if (mode >= 1) {

@@ -103,13 +103,34 @@ def test_sc3_mapping_variants(cw, ctas, n, monkeypatch):
     assert np.array_equal(u_info.cpu().numpy().astype(np.uint8), ref[:, po.info_positions(fp, n)])
 
 
+@pytest.mark.parametrize("warps,n,B", [(0, 128, 5000), (3, 256, 3001), (0, 512, 2000), (0, 1024, 9000), (1, 1024, 100),
+                                       (5, 1024, 4097), (7, 1024, 31), (0, 2048, 1500), (2, 2048, 700)])
+def test_sc4_warp_autonomous_variants(warps, n, B, monkeypatch):
+    """polar_sc4.cu (default mapping): a warp per 32 codewords, tensor-memory scratch for n >= 1024."""
+    import torch
+    from oracle import polar_oracle as po, c_oracle as co
+    dk = _dk()
+    k = n // 2
+    monkeypatch.setenv("POLAR_SC_MODE", "3")
+    monkeypatch.setenv("POLAR_SC_WARPS_SM", str(warps))
+    fp = po.rm_frozen_pos(n, n - k)
+    _, logits = awgn_logits(np.random.default_rng(warps + n), n, k, fp, B, 3.0)
+    logits[::9] = np.round(logits[::9])
+    ref = co.sc_decode_full(logits, po.frozen_vec(fp, n))
+    tables = dk.code_tables(fp, n, torch.device("cuda", 0))
+    u_info, u_packed = dk.sc_decode(torch.from_numpy(logits).cuda(), tables, want_info=True, want_packed=True)
+    assert np.array_equal(unpack_words(u_packed.cpu().numpy(), n), ref)
+    assert np.array_equal(u_info.cpu().numpy().astype(np.uint8), ref[:, po.info_positions(fp, n)])
+
+
+@pytest.mark.parametrize("mode", [2, 3])
 @pytest.mark.parametrize("n", [128, 1024, 2048])
-def test_sc3_extreme_frozen_patterns(n, monkeypatch):
+def test_sc3_extreme_frozen_patterns(n, mode, monkeypatch):
     """rate-0 halves / quarters (virtual-stage corner cases), none frozen, single info bit, alternating, 5G-like."""
     import torch
     from oracle import polar_oracle as po, c_oracle as co
     dk = _dk()
-    monkeypatch.setenv("POLAR_SC_MODE", "2")
+    monkeypatch.setenv("POLAR_SC_MODE", str(mode))
     B = 333
     rng = np.random.default_rng(n)
     logits = (rng.standard_normal((B, n)) * 4).astype(np.float32)

@@ -47,6 +47,24 @@ def main():
                 best, med = timeit(f)
                 print("SC-CTA n=%d B=%d ctas/SM=%d threads=%3d: %8.3f ms  %.3e cw/s  %.1f Gbit/s info  HBM-frac %.3f" %
                       (n, B, ctas, thr, best, B / best * 1e3, B / best * 1e3 * k / 1e9, B / best * 1e3 * (4 * n + k / 8) / 6552.3e9), flush=True)
+    elif what == "sc4":
+        import ctypes
+        B = int(sys.argv[3]) if len(sys.argv) > 3 else (1 << 28) // n
+        _, _, x = dk.awgn_frontend(tables, B, no, 1234)
+        up = torch.empty((B, dk.words(n)), dtype=torch.int32, device=dev)
+        os.environ["POLAR_SC_MODE"] = "3"
+        for w in [int(v) for v in os.environ.get("WARPS", "0").split(",")]:
+            os.environ["POLAR_SC_WARPS_SM"] = str(w)
+            f = lambda: dk.check(dk.lib().polar_sc_decode_f32(dk.ptr(x), dk.ptr(tables.frozen_mask), n, B, dk.ptr(up), None, None, 0, dk.stream_ptr(dev)))
+            best, med = timeit(f)
+            if os.environ.get("POLAR_SC3_DBG") == "1":
+                L = ctypes.CDLL(dk.LIB_PATH); buf = (ctypes.c_ulonglong * 8)()
+                L.polar_sc4_debug_read(buf); f(); torch.cuda.synchronize(); L.polar_sc4_debug_read(buf)
+                v = list(buf); nb = max(v[7], 1)
+                print("  warp0 cycles/batch: virt %d  g %d  f %d  bottom %d  merge %d  out %d  | total %d  batches %d" %
+                      tuple([x // nb for x in v[:7]] + [v[7]]))
+            print("SC4 n=%d B=%d warps/SM=%d: %8.3f ms  %.3e cw/s  %.1f Gbit/s info  HBM-frac %.3f" %
+                  (n, B, w, best, B / best * 1e3, B / best * 1e3 * k / 1e9, B / best * 1e3 * (4 * n + k / 8) / 6552.3e9), flush=True)
     elif what == "sc3":
         B = int(sys.argv[3]) if len(sys.argv) > 3 else (1 << 28) // n
         _, _, x = dk.awgn_frontend(tables, B, no, 1234)
