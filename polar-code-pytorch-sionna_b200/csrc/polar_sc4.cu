@@ -39,11 +39,11 @@ struct Sc4Layout {
   int nw, nws, n64, top, stride;
   size_t nz_off, warp_off, per_warp, total;
 };
-__host__ __device__ inline Sc4Layout sc4_layout(int m, bool tm, int warps) {
+__host__ __device__ inline Sc4Layout sc4_layout(int m, int top, int warps) {
   Sc4Layout l;
   const int n = 1 << m;
   l.nw = n >> 5; l.nws = l.nw + 1; l.n64 = n >> 6;
-  l.top = tm ? m - 3 : m - 1;                         // highest stage kept in shared memory (>= 6)
+  l.top = top;                                        // highest stage kept in shared memory (>= 6)
   l.stride = (2 << l.top) - 64 + 4;                   // floats per codeword row (stages 6..top); stride/4 is odd
   l.nz_off = (size_t)((l.nw * 4 + 15) / 16) * 16;
   l.warp_off = l.nz_off + (size_t)((2 * l.n64 + 15) / 16) * 16 + 16;   // +16: tensor-memory base address slot
@@ -228,10 +228,46 @@ __device__ __noinline__ void step_virt_tmem(const int kind, const float *__restr
   tmem_wait_st();
 }
 
-// stage M-2 (tensor memory, lane-private pairs) -> stage M-3 in shared memory.
+// channel (global, stage M) -> stage M-1 in TENSOR MEMORY (n = 512: no virtual stage needed).
+// Work item p = lane + 32k = (codeword c, pair q): the float4 at elements 4q and 4q + H/2 of the stage M-1 node.
 template <int M, bool IS_G>
+__device__ __noinline__ void step_glob_tmem(const float *__restrict__ logit, int64_t cw0, int nvalid, const uint32_t *beta,
+                                            int nws, int lane, uint32_t tm_base) {
+  constexpr int N = 1 << M, H = N >> 1, PQ = H >> 3;   // PQ pairs per codeword (multiple of 32)
+  constexpr int KMAX = PQ, VU = 4;
+#pragma unroll 1
+  for (int k0 = 0; k0 < KMAX; k0 += VU) {
+    float4 a[VU][2], b[VU][2];
+#pragma unroll
+    for (int r = 0; r < VU; ++r) {
+      const int p = lane + 32 * (k0 + r);
+      const int c = (int)((unsigned)p / (unsigned)PQ), q = (int)((unsigned)p % (unsigned)PQ);
+      const int cl = c < nvalid ? c : nvalid - 1;
+      const float *row = logit + (cw0 + cl) * (int64_t)N + 4 * q;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) { a[r][e] = ldg4(row + e * (H / 2)); b[r][e] = ldg4(row + e * (H / 2) + H); }
+    }
+#pragma unroll
+    for (int r = 0; r < VU; ++r) {
+      const int p = lane + 32 * (k0 + r);
+      const int c = (int)((unsigned)p / (unsigned)PQ), q = (int)((unsigned)p % (unsigned)PQ);
+      float4 o[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = 4 * q + e * (H / 2);
+        if (IS_G) o[e] = g4neg(a[r][e], b[r][e], beta[c * nws + (j >> 5)] >> (j & 31));
+        else o[e] = f4(a[r][e], b[r][e]);                 // f(-a,-b) == f(a,b)
+      }
+      tmem_st8(tm_base + 8 * (k0 + r), o[0], o[1]);
+    }
+  }
+  tmem_wait_st();
+}
+
+// stage TS (tensor memory, lane-private pairs) -> stage TS-1 in shared memory.
+template <int TS, bool IS_G>   // TS = stage held in tensor memory; writes stage TS-1
 PDEV void step_tmem(float *L, const uint32_t *beta, int stride, int nws, int lane, uint32_t tm_base, int left_word) {
-  constexpr int N = 1 << M, H = N >> 3, PQ = H >> 2;   // H outputs per codeword = PQ float4
+  constexpr int H = 1 << (TS - 1), PQ = H >> 2;        // H outputs per codeword = PQ float4
   constexpr int KMAX = PQ;
   float *dst = L + (H - 64);
 #pragma unroll 2
@@ -282,17 +318,21 @@ PDEV uint2 bottom64(const float *node, uint32_t fm0, uint32_t fm1) {
   return make_uint2(bl ^ bc, bc);
 }
 
-template <int M, bool TM>
+// MODE 0: stages 6..M-1 in shared memory (n <= 256).  MODE 1: stage M-1 in tensor memory (n = 512).
+// MODE 2: stage M-1 virtual, stage M-2 in tensor memory (n >= 1024).
+template <int M, int MODE>
 __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ logit, const uint32_t *__restrict__ fmask_g,
                                                      int64_t B, int64_t nbatches, int l2_prefetch, int l2_hints, int dbg,
                                                      uint32_t *__restrict__ u_packed, float *__restrict__ u_info,
                                                      const int32_t *__restrict__ info_pos, int k) {
-  static_assert(TM ? (M >= 10 && M <= 11) : (M >= 7), "sc4: stage 6 must exist in shared memory; a warp reaches 512 TMEM columns");
+  constexpr bool TM = MODE >= 1, VIRT = MODE == 2;
+  constexpr int TS = VIRT ? M - 2 : M - 1;                  // stage held in tensor memory (TM only)
+  static_assert(MODE == 0 ? (M >= 7) : (TS >= 7 && TS <= 9), "sc4: stage 6 must exist in shared memory; a warp reaches 512 TMEM columns");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int N = 1 << M, NW = N >> 5, NWS = NW + 1, N64 = N >> 6, TOP = TM ? M - 3 : M - 1;
-  constexpr int TM_COLS_WARP = TM ? (1 << (M - 2)) : 32;    // 32 codewords x 2^(M-2) floats / 32 lanes
+  constexpr int N = 1 << M, NW = N >> 5, NWS = NW + 1, N64 = N >> 6, TOP = TM ? TS - 1 : M - 1;
+  constexpr int TM_COLS_WARP = TM ? (1 << TS) : 32;         // 32 codewords x 2^TS floats / 32 lanes
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const Sc4Layout lay = sc4_layout(M, TM, nwarps);
+  const Sc4Layout lay = sc4_layout(M, TOP, nwarps);
   constexpr int stride = (2 << TOP) - 64 + 4;    // == lay.stride, compile-time so that row offsets fold into immediates
   uint32_t *fmask = reinterpret_cast<uint32_t *>(smem_raw);
   unsigned char *nz = smem_raw + lay.nz_off;    // nz[(N64 >> lv) + (i >> lv)]: node of 2^lv 64-blocks at block i is rate-0
@@ -344,35 +384,39 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
         }
       }
       bool zeroed = nz[(N64 >> (S - 6)) + (i >> (S - 6))] != 0;
-      if (!zeroed && S < M && !(TM && S == M - 1)) {
+      if (!zeroed && S < M && !(VIRT && S == M - 1)) {
         // g step into (S, i) from its parent at stage S+1; the left sibling's beta starts at word 2*(i - 2^(S-6))
         const int left_word = 2 * (i - (1 << (S - 6)));
-        if (TM && S == M - 2) {
+        if (VIRT && S == M - 2) {
           step_virt_tmem<M>(i < N64 / 2 ? 1 : 3, logit, cw0, nvalid, beta, NWS, lane, tm_base, l2_hints);
-        } else if (TM && S == M - 3) {
-          step_tmem<M, true>(L, beta, stride, NWS, lane, tm_base, left_word);
+        } else if (TM && !VIRT && S == M - 1) {
+          step_glob_tmem<M, true>(logit, cw0, nvalid, beta, NWS, lane, tm_base);
+        } else if (TM && S == TS - 1) {
+          step_tmem<TS, true>(L, beta, stride, NWS, lane, tm_base, left_word);
         } else if (!TM && S == M - 1) {
           step_glob<M, true>(logit, cw0, nvalid, L, beta, stride, NWS, lane);
         } else {
           step_smem_any<TOP - 1, true>(S, L, beta, stride, NWS, lane, left_word);
         }
         __syncwarp();
-        SC4_T((TM && S == M - 2) ? 0 : 1);
+        SC4_T((VIRT && S == M - 2) ? 0 : 1);
       }
       while (!zeroed && s > 6) {
         if (nz[(N64 >> (s - 7)) + (i >> (s - 7))]) { zeroed = true; --s; break; }   // left child is rate-0
-        if (TM && s == M) { --s; continue; }                                           // virtual stage: nothing stored
-        if (TM && s == M - 1) {
+        if (VIRT && s == M) { --s; continue; }                                         // virtual stage: nothing stored
+        if (VIRT && s == M - 1) {
           step_virt_tmem<M>(i < N64 / 2 ? 0 : 2, logit, cw0, nvalid, beta, NWS, lane, tm_base, l2_hints);
-        } else if (TM && s == M - 2) {
-          step_tmem<M, false>(L, beta, stride, NWS, lane, tm_base, 0);
+        } else if (TM && !VIRT && s == M) {
+          step_glob_tmem<M, false>(logit, cw0, nvalid, beta, NWS, lane, tm_base);
+        } else if (TM && s == TS) {
+          step_tmem<TS, false>(L, beta, stride, NWS, lane, tm_base, 0);
         } else if (!TM && s == M) {
           step_glob<M, false>(logit, cw0, nvalid, L, beta, stride, NWS, lane);
         } else {
           step_smem_any<TOP - 1, false>(s - 1, L, beta, stride, NWS, lane, 0);
         }
         __syncwarp();
-        SC4_T((TM && s == M - 1) ? 0 : 2);
+        SC4_T((VIRT && s == M - 1) ? 0 : 2);
         --s;
       }
       const int lv0 = s - 6;                     // the finished node covers 2^lv0 64-blocks starting at i
@@ -446,17 +490,21 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
   }
 }
 
-template <int M, bool TM>
+template <int M, int MODE>
 int launch_sc4_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t *u_packed, float *u_info,
                  const int32_t *info_pos, int k, int warps, cudaStream_t st) {
   const int max_smem = device_max_smem_optin();
+  constexpr bool TM = MODE >= 1;
+  constexpr int TS = MODE == 2 ? M - 2 : M - 1;
   int wmax = 8;
-  if (TM) wmax = 4 * (512 >> (M - 2));          // TMEM columns: 2^(M-2) per warp, 512 per lane quarter
+  if (TM) wmax = 4 * (512 >> TS);               // TMEM columns: 2^TS per warp, 512 per lane quarter
+  if (wmax > 8) wmax = 8;
   if (warps <= 0 || warps > wmax) warps = wmax;
-  while (warps > 1 && sc4_layout(M, TM, warps).total > (size_t)max_smem) --warps;
-  const Sc4Layout lay = sc4_layout(M, TM, warps);
+  constexpr int TOP = TM ? TS - 1 : M - 1;
+  while (warps > 1 && sc4_layout(M, TOP, warps).total > (size_t)max_smem) --warps;
+  const Sc4Layout lay = sc4_layout(M, TOP, warps);
   if (lay.total > (size_t)max_smem) return set_error(POLAR_ENOMEM, "sc: n=%d needs %zu B shared memory per CTA", 1 << M, lay.total);
-  auto kern = sc4_kernel<M, TM>;
+  auto kern = sc4_kernel<M, MODE>;
   // one persistent CTA per SM.  With tensor memory the CTA takes all 512 columns, so a second CTA must never
   // become resident on the same SM: pad the request above half of the SM's shared memory.
   size_t smem = lay.total;
@@ -480,11 +528,11 @@ int launch_sc4_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t 
 int launch_sc4(const float *logit, const uint32_t *fmask, int n, int64_t B, uint32_t *u_packed, float *u_info,
                const int32_t *info_pos, int k, int warps, cudaStream_t st) {
   switch (ilog2(n)) {
-    case 7: return launch_sc4_t<7, false>(logit, fmask, B, u_packed, u_info, info_pos, k, warps, st);
-    case 8: return launch_sc4_t<8, false>(logit, fmask, B, u_packed, u_info, info_pos, k, warps, st);
-    case 9: return launch_sc4_t<9, false>(logit, fmask, B, u_packed, u_info, info_pos, k, warps, st);
-    case 10: return launch_sc4_t<10, true>(logit, fmask, B, u_packed, u_info, info_pos, k, warps, st);
-    case 11: return launch_sc4_t<11, true>(logit, fmask, B, u_packed, u_info, info_pos, k, warps, st);
+    case 7: return launch_sc4_t<7, 0>(logit, fmask, B, u_packed, u_info, info_pos, k, warps, st);
+    case 8: return launch_sc4_t<8, 0>(logit, fmask, B, u_packed, u_info, info_pos, k, warps, st);
+    case 9: return launch_sc4_t<9, 1>(logit, fmask, B, u_packed, u_info, info_pos, k, warps, st);
+    case 10: return launch_sc4_t<10, 2>(logit, fmask, B, u_packed, u_info, info_pos, k, warps, st);
+    case 11: return launch_sc4_t<11, 2>(logit, fmask, B, u_packed, u_info, info_pos, k, warps, st);
     default: return set_error(POLAR_EINVAL, "sc4: n=%d not supported by this mapping", n);
   }
 }
