@@ -105,7 +105,7 @@ def main():
         L = int(os.environ.get("L", "8"))
         B = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 15
         _, _, x = dk.awgn_frontend(tables, B, no, 1234)
-        for kb in [int(v) for v in os.environ.get("KBS", "72,40,24,12").split(",")]:
+        for kb in [int(v) for v in os.environ.get("KBS", "4").split(",")]:
             for warps in [int(v) for v in os.environ.get("WARPS", "1,2,4").split(",")]:
                 os.environ["POLAR_SCL_SMEM_KB"] = str(kb); os.environ["POLAR_SCL_WARPS"] = str(warps)
                 try:
