@@ -116,6 +116,18 @@ int polar_count_errors_packed(const uint32_t *d_a, const uint32_t *d_b, const ui
 int polar_count_errors_f32(const float *d_b, const float *d_b_hat, int k, int64_t B,
                            unsigned long long *d_counters, void *stream);
 
+/* ---- Monte-Carlo stop rules on the device ----------------------------------------------------------
+ * Replaces the per-iteration host logic of sim_ber (my_sn/sim.py:90-123): accumulate this iteration's counters
+ * and evaluate the target-bit-error / target-block-error / max-iteration rules in a one-thread kernel, so the
+ * host can keep iterations queued without reading counters back.
+ *  d_delta4  uint64[4]: (bit errors, block errors, bits, blocks) of the iteration (all-reduced over ranks when the
+ *            batch is sharded); cleared by the call.
+ *  d_state8  int64[8]: [0..3] running totals, [4] stop flag, [5] status (1 max iter, 3 bit target, 4 block target,
+ *            sim.py:63-66), [6] iterations counted, [7] reserved.  Once [4] is set, later calls only clear d_delta4.
+ *  target_* < 0: rule disabled. */
+int polar_mc_control(unsigned long long *d_delta4, long long *d_state8, long long target_bit_errs,
+                     long long target_block_errs, long long max_mc_iter, void *stream);
+
 /* ---- bit (un)packing helpers used by the Python mirror ---------------------------------------- */
 int polar_pack_bits_f32(const float *d_x /*[B,n] 0/1*/, int n, int64_t B, uint32_t *d_packed, void *stream);
 int polar_unpack_info_f32(const uint32_t *d_packed, const int32_t *d_pos /*[k]*/, int n, int k, int64_t B,

@@ -53,9 +53,37 @@ __global__ void __launch_bounds__(256) count_f32_kernel(const float *__restrict_
   }
 }
 
+// Stop rules of sim_ber (my_sn/sim.py:90-118) evaluated on the device, one thread.  state (int64[8]):
+// [0] bit errors [1] block errors [2] bits [3] blocks [4] stop flag [5] status code [6] iterations counted.
+// delta (uint64[4]): this iteration's (bit errors, block errors, bits, blocks), summed over ranks when sharded.
+// Once `stop` is set later iterations are ignored, so the host may enqueue iterations ahead of the counters.
+__global__ void mc_control_kernel(unsigned long long *__restrict__ delta, long long *__restrict__ state,
+                                  long long target_bit, long long target_block, long long max_iter) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (!state[4]) {
+    state[0] += (long long)delta[0]; state[1] += (long long)delta[1];
+    state[2] += (long long)delta[2]; state[3] += (long long)delta[3];
+    const long long it = ++state[6];
+    if (target_bit >= 0 && state[0] >= target_bit) { state[5] = 3; state[4] = 1; }             // sim.py:107-112
+    else if (target_block >= 0 && state[1] >= target_block) { state[5] = 4; state[4] = 1; }    // sim.py:113-118
+    else if (it >= max_iter) { state[5] = 1; state[4] = 1; }                                   // sim.py:120-123
+  }
+  delta[0] = 0; delta[1] = 0; delta[2] = 0; delta[3] = 0;
+}
+
 }  // namespace polar
 
 using namespace polar;
+
+extern "C" int polar_mc_control(unsigned long long *d_delta4, long long *d_state8, long long target_bit_errs,
+                                long long target_block_errs, long long max_mc_iter, void *stream) {
+  if (!d_delta4 || !d_state8) return set_error(POLAR_EINVAL, "mc_control: null pointer");
+  if (max_mc_iter < 1) return set_error(POLAR_EINVAL, "mc_control: max_mc_iter < 1");
+  mc_control_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_delta4, d_state8, target_bit_errs, target_block_errs, max_mc_iter);
+  count_launch();
+  POLAR_CHECK_LAUNCH("mc_control");
+  return POLAR_OK;
+}
 
 static unsigned cnt_grid(int64_t rows) {
   int64_t g = (rows + 7) / 8;

@@ -62,6 +62,20 @@ class SCL_Dec(nn.Module):
   @property
   def list_size(self): return self._list_size
 
+  def _rows_on(self, dev):
+    if not self._use_crc:
+      return None, 0
+    rows = self._crc_rows.get(str(dev))
+    if rows is None:
+      rows = self._crc_rows[str(dev)] = tc.from_numpy(self._crc_rows_np.view(np.int32).copy()).to(dev)
+    return rows, self._k_crc
+
+  def decode_packed(self, logits, tables):
+    """Device fast path of the on-device Monte-Carlo loop: bit-packed decisions of the (CRC-)selected path."""
+    rows, ln = self._rows_on(tables.dev)
+    return dk.scl_decode(logits, tables, self._list_size, crc_rows=rows, crc_len=ln, want_info=False,
+                         want_packed=True)["u_packed"]
+
   def forward(self, inputs):
     assert inputs.dtype == self.output_dtype, "Invalid input dtype."
     assert inputs.shape[-1] == self._n, "Last input dimension must be of length n."

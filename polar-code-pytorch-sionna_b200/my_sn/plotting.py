@@ -21,10 +21,11 @@ class PlotBER():
     self.ber = []; self.snr = []; self.legend = []
 
   def simulate(self, mc_fun, ebno_dbs, batch_size, legend="", add_ber=True, add_bler=False, max_mc_iter=1,
-               soft_estimates=False, target_bit_errs=None, target_block_errs=None, verbose=True, device='cpu'):
+               soft_estimates=False, target_bit_errs=None, target_block_errs=None, verbose=True, device='cpu',
+               on_device=True):
     ber, bler = sim_ber(mc_fun, ebno_dbs, batch_size, soft_estimates=soft_estimates, max_mc_iter=max_mc_iter,
                         target_bit_errs=target_bit_errs, target_block_errs=target_block_errs, verbose=verbose,
-                        device=device)
+                        device=device, on_device=on_device)
     if add_ber:
       self.ber += [ber]; self.snr += [ebno_dbs]; self.legend += [legend]
     if add_bler:

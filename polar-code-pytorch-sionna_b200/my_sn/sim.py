@@ -5,7 +5,8 @@ fused kernel (`polar_count_errors_f32`) into a device counter pair and read back
 (the stop rules of sim.py:107-133 need them on the host); when `torch.distributed` is initialised the
 four counters are combined with one 4 x int64 all-reduce per iteration so every rank takes the same
 stop decisions.  `mc_fun` is then expected to simulate its shard (batch_size is the
-per-rank batch)."""
+per-rank batch).  When `mc_fun` is the fused AWGN link model, `sim_ber` hands over to `sim_ber_device`, which keeps
+the whole loop -- including the stop rules -- on the device."""
 import time
 
 import numpy as np
@@ -44,11 +45,109 @@ def _dist():
   return dist if (dist.is_available() and dist.is_initialized()) else None
 
 
+def _device_loop_ok(mc_fun, soft_estimates, count_fn):
+  """The on-device loop applies to the fused AWGN link model with a decoder that has the packed fast path."""
+  return (count_fn is None and not soft_estimates and getattr(mc_fun, "fused", False)
+          and not getattr(mc_fun, "cw_estimates", True) and hasattr(getattr(mc_fun, "decoder", None), "decode_packed")
+          and tc.cuda.is_available())
+
+
+def sim_ber_device(model, ebno_dbs, batch_size, max_mc_iter, target_bit_errs=None, target_block_errs=None,
+                   early_stop=True, verbose=True, return_counters=False):
+  """the Monte-Carlo loop of sim.py:79-133 with every per-iteration step on the device.
+
+  One iteration = front-end kernel (bits -> encoder -> QPSK -> AWGN -> logits) -> decoder kernel (bit-packed
+  decisions) -> packed error counter -> [sharded: one 4 x int64 NCCL all-reduce] -> `polar_mc_control`, a one-thread
+  kernel that accumulates the counters and evaluates the stop rules (target bit errors, target block errors, max
+  iterations).  The host never reads a counter inside an SNR point: it keeps ONE iteration queued ahead and only
+  polls the stop flag of the iteration before that from pinned memory, so the GPU is never idle; the iteration that
+  was queued past the stop is ignored by the control kernel (and its random numbers are handed to the next point),
+  which makes the result identical to the host loop (`sim_ber(..., on_device=False)`) for the same seed.
+  Returns (ber, bler) like sim_ber; with return_counters also the int64 [P,4] counters, status and iterations."""
+  dist = _dist()
+  rank0 = dist is None or dist.get_rank() == 0
+  verbose = verbose and rank0
+  dev = dk.cuda_device(model.device)
+  dec = model.decoder
+  frozen_pos = getattr(model.encoder, "frozen_pos", None)
+  if frozen_pos is None:
+    frozen_pos = dec.frozen_pos
+  tables = dk.code_tables(frozen_pos, model.n, dev)
+  if model._seed is None:
+    model._seed = int(tc.randint(0, 2 ** 62, (1,)).item())
+  from my_sn.trans import ebno as _ebno
+  ebno_dbs = np.asarray(ebno_dbs, dtype=np.float32)
+  P = ebno_dbs.shape[0]
+  B = int(batch_size)
+  counters = np.zeros((P, 4), dtype=np.int64)
+  status = np.zeros(P, dtype=np.int64)
+  iters = np.zeros(P, dtype=np.int64)
+  runtime = np.zeros(P)
+  status_levels = ["not simulated", "reached max iter       ", "no errors - early stop",
+                   "reached target bit errors", "reached target block errors"]
+  fmt = "{: >9} |{: >11} |{: >11} |{: >12} |{: >12} |{: >13} |{: >12} |{: >12} |{: >10}"
+  with tc.cuda.device(dev):
+    state = tc.zeros(8, dtype=tc.int64, device=dev)
+    delta = tc.zeros(4, dtype=tc.int64, device=dev)
+    sizes = tc.tensor([0, 0, B * tables.k, B], dtype=tc.int64, device=dev)
+    host = [tc.zeros(8, dtype=tc.int64).pin_memory() for _ in range(2)]
+    events = [tc.cuda.Event() for _ in range(2)]
+    for i in range(P):
+      t0 = time.perf_counter()
+      no = _ebno.ebnodb2no(float(ebno_dbs[i]), model.n_bits_per_sym, model.coderate)
+      state.zero_()
+      offset0 = model._offset
+      for ii in range(max_mc_iter):
+        u_tx, _, llr = dk.awgn_frontend(tables, B, no, model._seed, offset0 + ii * B)
+        u_hat = dec.decode_packed(llr, tables)
+        delta.copy_(sizes)                                     # (0, 0, bits, blocks) of this rank's shard
+        dk.count_errors_packed(u_tx, u_hat, tables.info_mask, model.n, delta)
+        if dist is not None:
+          dist.all_reduce(delta)                               # stream-ordered NCCL all-reduce of 4 x int64
+        dk.mc_control(delta, state, target_bit_errs, target_block_errs, max_mc_iter)
+        host[ii & 1].copy_(state, non_blocking=True)
+        events[ii & 1].record()
+        if ii >= 1:                                            # poll the iteration BEFORE the one just queued
+          events[(ii - 1) & 1].synchronize()
+          if int(host[(ii - 1) & 1][4]):
+            break
+      tc.cuda.current_stream(dev).synchronize()
+      st = state.cpu().numpy()
+      counters[i] = st[:4]; status[i] = st[5]; iters[i] = st[6]
+      model._offset = offset0 + int(st[6]) * B                 # random numbers of a discarded iteration are reused
+      runtime[i] = time.perf_counter() - t0
+      if verbose:
+        if i == 0:
+          print(fmt.format("EbNo [dB]", "BER", "BLER", "bit errors", "num bits", "block errors", "num blocks",
+                           "runtime [s]", "status")); print('-' * 135)
+        ber_i = counters[i, 0] / counters[i, 2] if counters[i, 2] else 0.0
+        bler_i = counters[i, 1] / counters[i, 3] if counters[i, 3] else 0.0
+        print(fmt.format(str(np.round(ebno_dbs[i], 3)), f"{ber_i:.4e}", f"{bler_i:.4e}", int(counters[i, 0]),
+                         int(counters[i, 2]), int(counters[i, 1]), int(counters[i, 3]), np.round(runtime[i], 1),
+                         status_levels[int(status[i])]))
+      if early_stop and counters[i, 1] == 0:                   # sim.py:128-133
+        status[i] = 2
+        if verbose:
+          print(f"\nSimu stopped as no error occurred @ EbNo = {ebno_dbs[i]:.1f} dB.\n")
+        break
+  with np.errstate(divide='ignore', invalid='ignore'):
+    ber = np.nan_to_num(counters[:, 0] / counters[:, 2])
+    bler = np.nan_to_num(counters[:, 1] / counters[:, 3])
+  out = (tc.from_numpy(ber.astype(np.float32)), tc.from_numpy(bler.astype(np.float32)))
+  if return_counters:
+    return out + (counters, status, iters)
+  return out
+
+
 def sim_ber(mc_fun, ebno_dbs, batch_size, max_mc_iter, soft_estimates=False, target_bit_errs=None,
-            target_block_errs=None, early_stop=True, verbose=True, dtype=tc.complex64, device='cpu', count_fn=None):
+            target_block_errs=None, early_stop=True, verbose=True, dtype=tc.complex64, device='cpu', count_fn=None,
+            on_device=True):
   """Returns (ber, bler) per SNR point; same stop rules and status codes as sim.py:19-140.
   `count_fn(b, b_hat) -> (bit_errors, block_errors)` defaults to the CUDA counter kernel; it exists so the
   sharding / stop logic can be exercised with a test double on machines without a GPU."""
+  if on_device and _device_loop_ok(mc_fun, soft_estimates, count_fn):
+    return sim_ber_device(mc_fun, ebno_dbs, batch_size, max_mc_iter, target_bit_errs=target_bit_errs,
+                          target_block_errs=target_block_errs, early_stop=early_stop, verbose=verbose)
   count_fn = count_fn or _count
   dist = _dist()
   rank0 = dist is None or dist.get_rank() == 0

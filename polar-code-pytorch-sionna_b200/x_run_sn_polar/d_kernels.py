@@ -54,6 +54,7 @@ _SIGNATURES = {
   "polar_qpsk_awgn_llr": (_i32, [_u64, _u64, _f32, _vp, _i32, _i64, _vp, _vp]),
   "polar_count_errors_packed": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
   "polar_count_errors_f32": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp]),
+  "polar_mc_control": (_i32, [_vp, _vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _vp]),
   "polar_pack_bits_f32": (_i32, [_vp, _i32, _i64, _vp, _vp]),
   "polar_unpack_info_f32": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp]),
   "polar_sc_decode_host": (_i32, [_vp, _vp, _i32, _i64, _vp, _i32]),
@@ -296,6 +297,15 @@ def count_errors_packed(a, b, mask, n, counters):
   with tc.cuda.device(dev):
     check(lib().polar_count_errors_packed(ptr(a.contiguous()), ptr(b.contiguous()), ptr(mask), int(n), a.shape[0],
                                           ptr(counters), stream_ptr(dev)))
+
+
+def mc_control(delta, state, target_bit_errs, target_block_errs, max_mc_iter):
+  """polar_mc_control: fold `delta` (int64[4]) into `state` (int64[8]) and evaluate sim_ber's stop rules on the device."""
+  dev = state.device
+  tb = -1 if target_bit_errs is None else int(target_bit_errs)
+  tk = -1 if target_block_errs is None else int(target_block_errs)
+  with tc.cuda.device(dev):
+    check(lib().polar_mc_control(ptr(delta), ptr(state), tb, tk, int(max_mc_iter), stream_ptr(dev)))
 
 
 def launch_count():

@@ -47,6 +47,10 @@ class SCL_Dec(nn.Module):
   @property
   def llr_max(self): return self._llr_max
 
+  def decode_packed(self, logits, tables):
+    """Device fast path of the on-device Monte-Carlo loop: bit-packed decisions of the best path."""
+    return dk.scl_decode(logits, tables, self._list_size, want_info=False, want_packed=True)["u_packed"]
+
   def forward(self, inputs):
     assert inputs.dtype == self.output_dtype, "Invalid input dtype."
     assert inputs.shape[-1] == self._n, "Last input dim must be of len n."

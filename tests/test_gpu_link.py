@@ -2,6 +2,8 @@
 reference draws from torch's CPU mt19937, the kernel from Philox), error counters, CRC-aided list
 decoding, the link model + Monte-Carlo loop (BER/BLER inside confidence intervals of the oracle),
 and the host-buffer C-ABI entry points."""
+import os
+
 import numpy as np
 import pytest
 
@@ -250,3 +252,71 @@ def test_full_size_properties_sc():
     # bit-exact vs the oracle on a slice of the full-size batch
     sl = slice(B - 3000, B)
     assert np.array_equal(unpack_words(hat[sl].cpu().numpy(), n), co.sc_decode_full(lg[sl].cpu().numpy(), po.frozen_vec(fp, n)))
+
+
+@pytest.mark.parametrize("dec_kind", ["sc", "scl4", "scl8_crc"])
+def test_on_device_monte_carlo_loop_equals_host_loop(dec_kind):
+    """sim_ber_device (stop rules evaluated by polar_mc_control on the GPU, one iteration queued ahead)
+    must reproduce the host loop counter for counter -- same seed, same number of counted iterations, same status."""
+    torch, dk, po, co, dev = _env()
+    from polar.enc import PolarEncoder
+    from polar.polar_sc import SC_Dec
+    from polar.polar_scl import SCL_Dec
+    from my_sn.fec.polar.dec import SCL_Dec as SCL_CRC
+    from z_sys_model.awgn_model import System_AWGN_model
+    from my_sn.sim import sim_ber, sim_ber_device
+    n, k, bs = 128, 64, 3000
+    fp = po.rm_frozen_pos(n, n - k)
+    make = {"sc": lambda: SC_Dec(fp, n), "scl4": lambda: SCL_Dec(fp, n, 4),
+            "scl8_crc": lambda: SCL_CRC(fp, n, 8, crc_degree="CRC6")}[dec_kind]
+    ebnos = np.array([1.0, 2.5, 4.0, 5.5, 9.0, 10.0], dtype=np.float32)
+    for kw in (dict(max_mc_iter=7, target_block_errs=500), dict(max_mc_iter=5, target_bit_errs=2000),
+               dict(max_mc_iter=3), dict(max_mc_iter=1, target_block_errs=1)):
+        host = System_AWGN_model(n, k, PolarEncoder(fp, n, None), make(), seed=99)
+        devm = System_AWGN_model(n, k, PolarEncoder(fp, n, None), make(), seed=99)
+        ber_h, bler_h = sim_ber(host, ebnos, bs, verbose=False, on_device=False, **kw)
+        ber_d, bler_d, cnt, status, iters = sim_ber_device(devm, ebnos, bs, verbose=False, return_counters=True, **kw)
+        assert torch.equal(ber_h, ber_d) and torch.equal(bler_h, bler_d), (dec_kind, kw)
+        assert host._offset == devm._offset                       # same number of counted iterations
+        assert (iters <= kw["max_mc_iter"]).all()
+        # status codes follow sim.py:63-66 / 107-133
+        first = int(status[0])
+        assert first in (1, 3, 4)
+        if "target_block_errs" in kw and cnt[0, 1] >= kw["target_block_errs"]:
+            assert first == 4
+        if "target_bit_errs" in kw and cnt[0, 0] >= kw["target_bit_errs"]:
+            assert first == 3
+        # early stop: the sweep ends at the first error-free point, later points stay "not simulated"
+        zero = np.nonzero((cnt[:, 1] == 0) & (cnt[:, 3] > 0))[0]
+        if len(zero):
+            assert status[zero[0]] == 2 and (cnt[zero[0] + 1:] == 0).all()
+    # sim_ber routes to the device loop by default and PlotBER.simulate passes the switch through
+    a = System_AWGN_model(n, k, PolarEncoder(fp, n, None), make(), seed=5)
+    b = System_AWGN_model(n, k, PolarEncoder(fp, n, None), make(), seed=5)
+    from my_sn.plotting import PlotBER
+    r1 = PlotBER("a").simulate(a, ebnos[:3], bs, max_mc_iter=2, verbose=False)
+    r2 = PlotBER("b").simulate(b, ebnos[:3], bs, max_mc_iter=2, verbose=False, on_device=False)
+    assert torch.equal(r1[0], r2[0]) and torch.equal(r1[1], r2[1])
+
+
+def test_on_device_loop_with_process_group_of_one():
+    """The sharded path (stream-ordered NCCL all-reduce of the 4 counters before polar_mc_control) with world size 1."""
+    torch, dk, po, co, dev = _env()
+    import torch.distributed as dist
+    from polar.enc import PolarEncoder
+    from polar.polar_sc import SC_Dec
+    from z_sys_model.awgn_model import System_AWGN_model
+    from my_sn.sim import sim_ber_device
+    n, k, bs = 256, 128, 2000
+    fp = po.rm_frozen_pos(n, n - k)
+    ebnos = np.array([2.0, 4.0], dtype=np.float32)
+    ref = sim_ber_device(System_AWGN_model(n, k, PolarEncoder(fp, n, None), SC_Dec(fp, n), seed=3), ebnos, bs, 3,
+                         target_block_errs=100, verbose=False, return_counters=True)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29731")
+    dist.init_process_group("nccl", rank=0, world_size=1)
+    try:
+        got = sim_ber_device(System_AWGN_model(n, k, PolarEncoder(fp, n, None), SC_Dec(fp, n), seed=3), ebnos, bs, 3,
+                             target_block_errs=100, verbose=False, return_counters=True)
+    finally:
+        dist.destroy_process_group()
+    assert np.array_equal(ref[2], got[2]) and np.array_equal(ref[3], got[3])
