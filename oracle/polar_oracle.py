@@ -116,6 +116,39 @@ def sc_decode_full(logits, frozen):
     return u
 
 
+def _f32_boxplus(a, b):
+    """my_sn/fec/polar/dec.py:33-46: clip to +-30, ln(1+e^(x+y)) - ln(e^x+e^y), fp32 like the reference's torch ops."""
+    a = np.clip(a, -LLR_MAX, LLR_MAX).astype(np.float32)
+    b = np.clip(b, -LLR_MAX, LLR_MAX).astype(np.float32)
+    out = np.log(np.float32(1) + np.exp(a + b)).astype(np.float32)
+    out -= np.log(np.exp(a) + np.exp(b)).astype(np.float32)
+    return out.astype(np.float32)
+
+
+def sc_decode_boxplus_full(logits, frozen):
+    """Sionna-style SC (my_sn/fec/polar/dec.py:47-157): sc_decode_full with the exact boxplus f.  SECONDARY oracle:
+    numpy's exp/log are not the reference's (torch) nor CUDA's, so it is compared statistically, never bit-exactly."""
+    llr = (np.float32(-1.0) * np.asarray(logits, dtype=np.float32))
+    B, n = llr.shape
+    u = np.zeros((B, n), dtype=np.uint8)
+
+    def rec(a, L):
+        ln = L.shape[1]
+        if ln == 1:
+            if frozen[a]:
+                return np.zeros((B, 1), dtype=np.uint8)
+            bit = (L[:, 0] <= 0).astype(np.uint8)
+            u[:, a] = bit
+            return bit[:, None]
+        h = ln // 2
+        bl = rec(a, _f32_boxplus(L[:, :h], L[:, h:]))
+        br = rec(a + h, _g32(L[:, :h], L[:, h:], bl))
+        return np.concatenate([bl ^ br, br], axis=1)
+
+    rec(0, llr)
+    return u
+
+
 def sc_decode(logits, frozen_pos, n):
     """SC_Dec.forward (polar_sc.py:113-133): [B, n] logits -> [B, k] fp32 bits at ascending info_pos."""
     fz = frozen_vec(frozen_pos, n)

@@ -3,6 +3,7 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+#include <math.h>
 
 #if defined(__CUDACC__)
 #define PHD __host__ __device__ __forceinline__
@@ -35,6 +36,18 @@ PHD float u2f(uint32_t u) {
 // |clip(x)| = min(|x|,30), so the magnitude is min(|a|,|b|,30); the sign is the xor of the sign
 // bits.  When an input is +-0 the reference yields +-0 (sign(0)=0); so does this (sign of a zero
 // LLR is never observable: the leaf rule is llr<=0 -> 1 and g adds it).
+#if defined(POLAR_F_BOXPLUS)
+// Exact boxplus f of the Sionna-style decoders (my_sn/fec/polar/dec.py:33-46), fp32 like the
+// reference's torch ops: clip both inputs to +-30, ln(1+e^(x+y)) - ln(e^x + e^y).  Selected per translation unit by
+// polar_bp_wrap.cu, which compiles the SC kernels a second time into namespace polar_bp.  expf/logf are the
+// accurate CUDA versions (<= 2 ulp); the CPU reference uses its own libm, so parity for this mode is statistical
+// (decisions differ only where the boxplus difference cancels to rounding noise).
+PHD float f_minsum(float a, float b) {
+  const float x = fminf(fmaxf(a, -kLlrMax), kLlrMax), y = fminf(fmaxf(b, -kLlrMax), kLlrMax);
+  return logf(1.0f + expf(x + y)) - logf(expf(x) + expf(y));
+}
+PHD float f_minsum_noclip(float a, float b) { return f_minsum(a, b); }
+#else
 // The sign is taken from the product a*b (IEEE: sign(a*b) = sign(a) xor sign(b), also for zero, underflowed
 // and infinite products): FMUL issues on the FMA pipe, which this integer-heavy decoder leaves idle, instead
 // of a third ALU-pipe instruction.  (inf*0 = NaN only arises with magnitude 0, where the sign is unobservable.)
@@ -57,6 +70,14 @@ PHD float f_minsum_noclip(float a, float b) {
 #endif
   return u2f(f2u(mag) | sgn);
 }
+#endif
+// f on LOGITS (LLR = -logit, polar_sc.py:122): for min-sum the negation cancels exactly (sign.sign, |.|); the
+// boxplus variant negates explicitly so that its exp/log see the same arguments as the reference's.
+#if defined(POLAR_F_BOXPLUS)
+PHD float f_minsum_neg(float a, float b) { return f_minsum(-a, -b); }
+#else
+PHD float f_minsum_neg(float a, float b) { return f_minsum(a, b); }
+#endif
 // g: (1-2u).a + b, unclipped, one rounding (polar_sc.py:49-53).  signmask = u ? 0x80000000 : 0.
 PHD float g_minsum(float a, float b, uint32_t signmask) { return u2f(f2u(a) ^ signmask) + b; }
 

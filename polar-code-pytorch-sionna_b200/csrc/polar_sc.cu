@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(256) sc_tree_kernel(const float *__restrict__ 
             const float4 *row = reinterpret_cast<const float4 *>(logit + (cw0 + cl) * (int64_t)n);
             float4 a = __ldg(row + (j >> 2)), b = __ldg(row + ((j + h) >> 2));
             float4 o;   // f(-a,-b) == f(a,b): the negation cancels in sign.sign and |.|
-            o.x = f_minsum(a.x, b.x); o.y = f_minsum(a.y, b.y);
-            o.z = f_minsum(a.z, b.z); o.w = f_minsum(a.w, b.w);
+            o.x = f_minsum_neg(a.x, b.x); o.y = f_minsum_neg(a.y, b.y);
+            o.z = f_minsum_neg(a.z, b.z); o.w = f_minsum_neg(a.w, b.w);
             *reinterpret_cast<float4 *>(dst + c * stride + j) = o;
           }
         } else {
@@ -294,6 +294,8 @@ __device__ __forceinline__ void sc_top_step(const float *__restrict__ logit, int
       o.y = g_minsum(a.y, b.y, (bits << 30) & 0x80000000u);
       o.z = g_minsum(a.z, b.z, (bits << 29) & 0x80000000u);
       o.w = g_minsum(a.w, b.w, (bits << 28) & 0x80000000u);
+    } else if (FROM_GLOBAL) {
+      o.x = f_minsum_neg(a.x, b.x); o.y = f_minsum_neg(a.y, b.y); o.z = f_minsum_neg(a.z, b.z); o.w = f_minsum_neg(a.w, b.w);
     } else {
       o.x = f_minsum(a.x, b.x); o.y = f_minsum(a.y, b.y); o.z = f_minsum(a.z, b.z); o.w = f_minsum(a.w, b.w);
     }
@@ -490,9 +492,9 @@ extern "C" int polar_sc_decode_f32(const float *d_logit, const uint32_t *d_froze
   }
   const int mode = env_int("POLAR_SC_MODE", 3);
   if (mode == 3 && n >= 128 && n <= 2048)   // default: warp-autonomous decoder, tensor memory scratch (polar_sc4.cu)
-    return launch_sc4(d_logit, d_frozen_mask, n, B, d_u_packed, d_u_info_f32, d_info_pos, k, env_int("POLAR_SC_WARPS_SM", 0), st);
+    return polar::launch_sc4(d_logit, d_frozen_mask, n, B, d_u_packed, d_u_info_f32, d_info_pos, k, env_int("POLAR_SC_WARPS_SM", 0), st);
   if (mode >= 2 && n >= 128)   // default: compile-time tree, virtual top stage, 64-leaf register subtrees (polar_sc3.cu)
-    return launch_sc3(d_logit, d_frozen_mask, n, B, d_u_packed, d_u_info_f32, d_info_pos, k, env_int("POLAR_SC_CTA_CW", 32),
+    return polar::launch_sc3(d_logit, d_frozen_mask, n, B, d_u_packed, d_u_info_f32, d_info_pos, k, env_int("POLAR_SC_CTA_CW", 32),
                       env_int("POLAR_SC_CTAS", 0), st);
   if (mode >= 1) {
     // CTA mapping (default): up to 32 codewords per CTA, `ctas` CTAs per SM

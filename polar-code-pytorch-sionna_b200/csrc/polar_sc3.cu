@@ -74,6 +74,11 @@ PDEV float4 f4(const float4 a, const float4 b) {
   return o;
 }
 // g on four consecutive elements; bit e of `bits` is the partial sum of element e
+PDEV float4 f4neg(const float4 a, const float4 b) {   // f on logits (see f_minsum_neg)
+  float4 o;
+  o.x = f_minsum_neg(a.x, b.x); o.y = f_minsum_neg(a.y, b.y); o.z = f_minsum_neg(a.z, b.z); o.w = f_minsum_neg(a.w, b.w);
+  return o;
+}
 PDEV float4 g4(const float4 a, const float4 b, const uint32_t bits) {
   float4 o;
   o.x = g_minsum(a.x, b.x, (bits << 31) & 0x80000000u);
@@ -163,7 +168,7 @@ __device__ __noinline__ void step_glob(const float *__restrict__ logit, int64_t 
         const int c = (int)((unsigned)it / (unsigned)HQ), j = (int)((unsigned)it % (unsigned)HQ) << 2;
         float4 o;
         if (IS_G) o = g4neg(a[r], b[r], beta[c * nws + (j >> 5)] >> (j & 31));
-        else o = f4(a[r], b[r]);                          // f(-a,-b) == f(a,b)
+        else o = f4neg(a[r], b[r]);                       // f(-a,-b) == f(a,b) for min-sum
         sts4(dst + c * stride + j, o);
       }
     }
@@ -202,7 +207,7 @@ __device__ __noinline__ void step_virt_tmem(const int kind, const float *__restr
       const int sh = j & 31;
       float4 y0, y1;
       if (!right) {              // left half of the codeword: stage M-1 node = f(channel)
-        y0 = f4(c0[e], c2[e]); y1 = f4(c1[e], c3[e]);
+        y0 = f4neg(c0[e], c2[e]); y1 = f4neg(c1[e], c3[e]);
       } else {                   // right half: stage M-1 node = g(channel, beta of the left half)
         y0 = g4neg(c0[e], c2[e], bw[0] >> sh); y1 = g4neg(c1[e], c3[e], bw[HW] >> sh);
       }

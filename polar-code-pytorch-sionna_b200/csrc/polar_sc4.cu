@@ -76,6 +76,11 @@ PDEV float4 f4(const float4 a, const float4 b) {
   o.x = f_minsum(a.x, b.x); o.y = f_minsum(a.y, b.y); o.z = f_minsum(a.z, b.z); o.w = f_minsum(a.w, b.w);
   return o;
 }
+PDEV float4 f4neg(const float4 a, const float4 b) {   // f on logits (see f_minsum_neg)
+  float4 o;
+  o.x = f_minsum_neg(a.x, b.x); o.y = f_minsum_neg(a.y, b.y); o.z = f_minsum_neg(a.z, b.z); o.w = f_minsum_neg(a.w, b.w);
+  return o;
+}
 PDEV float4 g4(const float4 a, const float4 b, const uint32_t bits) {   // bit e of `bits` = partial sum of element e
   float4 o;
   o.x = g_minsum(a.x, b.x, (bits << 31) & 0x80000000u);
@@ -167,7 +172,7 @@ __device__ __noinline__ void step_glob(const float *__restrict__ logit, int64_t 
       const int c = (int)((unsigned)it / (unsigned)HQ), j = (int)((unsigned)it % (unsigned)HQ) << 2;
       float4 o;
       if (IS_G) o = g4neg(a[r], b[r], beta[c * nws + (j >> 5)] >> (j & 31));
-      else o = f4(a[r], b[r]);                          // f(-a,-b) == f(a,b)
+      else o = f4neg(a[r], b[r]);                       // f(-a,-b) == f(a,b) for min-sum
       sts4(dst + c * stride + j, o);
     }
   }
@@ -215,7 +220,7 @@ __device__ __noinline__ void step_virt_tmem(const int kind, const float *__restr
         const int sh = j & 31;
         float4 y0, y1;
         if (!right) {              // left half of the codeword: stage M-1 node = f(channel)
-          y0 = f4(c0[r][e], c2[r][e]); y1 = f4(c1[r][e], c3[r][e]);
+          y0 = f4neg(c0[r][e], c2[r][e]); y1 = f4neg(c1[r][e], c3[r][e]);
         } else {                   // right half: stage M-1 node = g(channel, beta of the left half)
           y0 = g4neg(c0[r][e], c2[r][e], bw[0] >> sh); y1 = g4neg(c1[r][e], c3[r][e], bw[HW] >> sh);
         }
@@ -256,7 +261,7 @@ __device__ __noinline__ void step_glob_tmem(const float *__restrict__ logit, int
       for (int e = 0; e < 2; ++e) {
         const int j = 4 * q + e * (H / 2);
         if (IS_G) o[e] = g4neg(a[r][e], b[r][e], beta[c * nws + (j >> 5)] >> (j & 31));
-        else o[e] = f4(a[r][e], b[r][e]);                 // f(-a,-b) == f(a,b)
+        else o[e] = f4neg(a[r][e], b[r][e]);              // f(-a,-b) == f(a,b) for min-sum
       }
       tmem_st8(tm_base + 8 * (k0 + r), o[0], o[1]);
     }

@@ -1,15 +1,52 @@
 """my_sn decoders (my_sn/fec/polar/dec.py).  Built this round: the CRC-aided SCL decoder
 (dec.py:158-537, selection logic :507-527) on the min-sum list kernel -- the composed oracle of
-SURVEY 8(c) for BASELINE config 3.  The reference's my_sn variant evaluates f with the exact boxplus
-and prunes rate-0/REP nodes; that arithmetic is SURVEY 8(f) row N2 and is NOT built yet (documented in
-DESIGN.md); `use_fast_scl` / `use_hybrid_sc` are accepted and ignored like dec.py:237-238."""
+SURVEY 8(c) for BASELINE config 3.  `SC_Dec` below is the Sionna-style boxplus SC decoder
+(dec.py:13-157).  The reference's my_sn SCL variant also evaluates f with the exact boxplus and prunes
+rate-0/REP nodes; that part of N2 is not built (documented in DESIGN.md); `use_fast_scl` / `use_hybrid_sc` are accepted
+and ignored like dec.py:237-238."""
 import numpy as np
 import torch as tc
 from torch import nn
 
 import d_kernels as dk
 from my_sn.fec.crc import CRCEncoder, CRCDecoder
-from polar.polar_sc import SC_Dec  # noqa: F401  (min-sum SC; the boxplus SC of dec.py:13-157 is row N2)
+
+
+class SC_Dec(nn.Module):
+  """Sionna-style SC decoder (my_sn/fec/polar/dec.py:13-157): same tree walk and leaf rule as the x_run SC_Dec,
+  but the check-node update is the exact boxplus ln(1+e^(x+y)) - ln(e^x+e^y) on inputs clipped to +-30 (dec.py:33-46).
+  Runs `polar_sc_decode_boxplus_f32` (the SC kernels compiled a second time with that f, csrc/polar_bp_wrap.cu).
+  Parity with the CPU reference is statistical for this decoder (SURVEY 8c "secondary oracle")."""
+
+  def __init__(self, frozen_pos, n, output_dtype=tc.float32, device='cpu'):
+    super().__init__()
+    self.output_dtype = output_dtype
+    self.n = n
+    self.frozen_pos = frozen_pos
+    self.k = self.n - len(self.frozen_pos)
+    self.info_pos = np.setdiff1d(np.arange(self.n), dk.to_numpy_pos(frozen_pos))
+    assert self.k == len(self.info_pos), "Internal error: invalid " "info_pos generated."
+    self.llr_max = 30.
+    self._frozen_ind = np.zeros(self.n)
+    self._frozen_ind[dk.to_numpy_pos(frozen_pos)] = 1
+    self._use_fast_sc = False
+    self.device = device
+
+  def decode_packed(self, logits, tables):
+    return dk.sc_decode(logits, tables, want_info=False, want_packed=True, boxplus=True)[1]
+
+  def forward(self, inputs):
+    assert inputs.shape[-1] == self.n, "Last input dim must be of len n."
+    assert len(inputs.shape) > 1
+    dev = inputs.device if inputs.is_cuda else dk.cuda_device(self.device)
+    tables = dk.code_tables(self.frozen_pos, self.n, dev)
+    u_hat, _ = dk.sc_decode(inputs, tables, want_info=True, boxplus=True)
+    output_shape = list(inputs.shape)
+    output_shape[-1] = self.k
+    output_shape[0] = -1
+    out = u_hat.reshape(output_shape).to(dtype=self.output_dtype)
+    return out if inputs.is_cuda else out.to(inputs.device)
+
 
 
 class SCL_Dec(nn.Module):

@@ -46,6 +46,7 @@ _SIGNATURES = {
   "polar_version": (ctypes.c_char_p, []),
   "polar_launch_count": (ctypes.c_ulonglong, []),
   "polar_sc_decode_f32": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _i32, _vp]),
+  "polar_sc_decode_boxplus_f32": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _i32, _vp]),
   "polar_scl_workspace_bytes": (_sz, [_i32, _i32, _i64]),
   "polar_scl_decode": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
   "polar_encode_packed": (_i32, [_vp, _i32, _i64, _vp, _vp]),
@@ -176,16 +177,18 @@ def _prep_logits(x, n, dev):
   return x
 
 
-def sc_decode(logits, tables, want_info=True, want_packed=False):
-  """polar_sc_decode_f32.  logits [B,n] (any float dtype/device) -> (u_info fp32 [B,k] | None, u_packed int32 | None)."""
+def sc_decode(logits, tables, want_info=True, want_packed=False, boxplus=False):
+  """polar_sc_decode_f32 (min-sum f) or polar_sc_decode_boxplus_f32 (exact boxplus f, my_sn SC_Dec).
+  logits [B,n] (any float dtype/device) -> (u_info fp32 [B,k] | None, u_packed int32 | None)."""
   dev = tables.dev
   x = _prep_logits(logits, tables.n, dev)
   B = x.shape[0]
   u_info = tc.empty((B, tables.k), dtype=tc.float32, device=dev) if want_info else None
   u_packed = tc.empty((B, words(tables.n)), dtype=tc.int32, device=dev) if want_packed else None
   with tc.cuda.device(dev):
-    check(lib().polar_sc_decode_f32(ptr(x), ptr(tables.frozen_mask), tables.n, B, ptr(u_packed), ptr(u_info),
-                                    ptr(tables.info_pos), tables.k, stream_ptr(dev)))
+    fn = lib().polar_sc_decode_boxplus_f32 if boxplus else lib().polar_sc_decode_f32
+    check(fn(ptr(x), ptr(tables.frozen_mask), tables.n, B, ptr(u_packed), ptr(u_info), ptr(tables.info_pos), tables.k,
+             stream_ptr(dev)))
   return u_info, u_packed
 
 
