@@ -39,12 +39,12 @@ struct Sc4Layout {
   int nw, nws, n64, top, stride;
   size_t nz_off, warp_off, per_warp, total;
 };
-__host__ __device__ inline Sc4Layout sc4_layout(int m, int top, int warps) {
+__host__ __device__ inline Sc4Layout sc4_layout(int m, int top, int bot, int warps) {
   Sc4Layout l;
   const int n = 1 << m;
-  l.nw = n >> 5; l.nws = l.nw + 1; l.n64 = n >> 6;
+  l.nw = n >> 5; l.nws = l.nw + 1; l.n64 = n >> bot;    // n64: number of 2^bot-leaf blocks
   l.top = top;                                        // highest stage kept in shared memory (>= 6)
-  l.stride = (2 << l.top) - 64 + 4;                   // floats per codeword row (stages 6..top); stride/4 is odd
+  l.stride = (2 << l.top) - (1 << bot) + 4;           // floats per codeword row (stages bot..top); stride/4 is odd
   l.nz_off = (size_t)((l.nw * 4 + 15) / 16) * 16;
   l.warp_off = l.nz_off + (size_t)((2 * l.n64 + 15) / 16) * 16 + 16;   // +16: tensor-memory base address slot
   l.per_warp = (((size_t)32 * l.stride * 4 + (size_t)32 * l.nws * 4) + 15) / 16 * 16;
@@ -125,11 +125,11 @@ PDEV float4 tm_hi(const Tm8 &v) { return make_float4(u2f(v.r[4]), u2f(v.r[5]), u
 
 // ---- cooperative steps of ONE warp over its 32 codewords ------------------------------------------
 // stage S+1 -> S inside shared memory.  out[j] = f(a[j], a[j+H]) or g(a[j], a[j+H], beta_left[j]).
-template <int S, bool IS_G>
+template <int S, bool IS_G, int BOT>
 PDEV void step_smem(float *L, const uint32_t *beta, int stride, int nws, int lane, int left_word) {
   constexpr int H = 1 << S, HQ = H >> 2, ITEMS = 32 * HQ;
-  float *dst = L + (H - 64);
-  const float *src = L + (2 * H - 64);
+  float *dst = L + (H - (1 << BOT));
+  const float *src = L + (2 * H - (1 << BOT));
 #pragma unroll 4
   for (int it = lane; it < ITEMS; it += 32) {
     const int c = (int)((unsigned)it / (unsigned)HQ), j = (int)((unsigned)it % (unsigned)HQ) << 2;
@@ -140,21 +140,21 @@ PDEV void step_smem(float *L, const uint32_t *beta, int stride, int nws, int lan
     sts4(dst + c * stride + j, o);
   }
 }
-template <int SMAX, bool IS_G>
+template <int SMAX, bool IS_G, int BOT>
 PDEV void step_smem_any(int s, float *L, const uint32_t *beta, int stride, int nws, int lane, int left_word) {
-  if constexpr (SMAX >= 6) {
-    if (s == SMAX) step_smem<SMAX, IS_G>(L, beta, stride, nws, lane, left_word);
-    else step_smem_any<SMAX - 1, IS_G>(s, L, beta, stride, nws, lane, left_word);
+  if constexpr (SMAX >= BOT) {
+    if (s == SMAX) step_smem<SMAX, IS_G, BOT>(L, beta, stride, nws, lane, left_word);
+    else step_smem_any<SMAX - 1, IS_G, BOT>(s, L, beta, stride, nws, lane, left_word);
   }
 }
 
 // channel (global, stage M) -> stage M-1 in shared memory (n <= 512: everything fits in shared memory).
-template <int M, bool IS_G>
+template <int M, bool IS_G, int BOT>
 __device__ __noinline__ void step_glob(const float *__restrict__ logit, int64_t cw0, int nvalid, float *L,
                                        const uint32_t *beta, int stride, int nws, int lane) {
   constexpr int N = 1 << M, H = N >> 1, HQ = H >> 2, ITEMS = 32 * HQ;
   constexpr int U = 4;        // items per round: 8 independent 128-bit loads in flight per lane
-  float *dst = L + (H - 64);
+  float *dst = L + (H - (1 << BOT));
 #pragma unroll 1
   for (int it0 = lane; it0 < ITEMS; it0 += U * 32) {
     float4 a[U], b[U];
@@ -186,15 +186,18 @@ template <int M>
 __device__ __noinline__ void step_virt_tmem(const int kind, const float *__restrict__ logit, int64_t cw0, int nvalid,
                                             const uint32_t *beta, int nws, int lane, uint32_t tm_base, int hints) {
   constexpr int N = 1 << M, H = N >> 2, PQ = H >> 3, HW = H >> 5;   // PQ pairs per codeword (multiple of 32)
-  // the row is read four times, a quarter of the decode apart: ask the L2 to keep it until the last pass
-  const uint64_t pol = !hints ? l2_policy_evict_normal() : (kind == 3) ? l2_policy_evict_first() : l2_policy_evict_last();
   constexpr int KMAX = PQ;                                          // 32 codewords * PQ pairs / 32 lanes
-  constexpr int VU = 4;                                             // pairs per round: 32 independent 128-bit loads in flight
+  constexpr int VU = 2;                                             // pairs per round; rounds are double buffered
+  // The row is read four times, a quarter of the decode apart, and the rows in flight (148 SMs x 8 warps x 32 x 4 KB)
+  // exceed the L2.  hints = 1: keep every row until its last pass (evict_last x3, evict_first).  hints = 2: only protect
+  // the pairs of passes that are a quarter apart (0->1 and 2->3), halving the protected set so that it fits.
+  const uint64_t pol = !hints ? l2_policy_evict_normal()
+                     : (hints == 2) ? ((kind & 1) ? l2_policy_evict_first() : l2_policy_evict_last())
+                                    : ((kind == 3) ? l2_policy_evict_first() : l2_policy_evict_last());
   const bool right = kind >= 2, is_g = kind & 1;
   const int gw = (kind == 3) ? 2 * HW : 0;
-#pragma unroll 1
-  for (int k0 = 0; k0 < KMAX; k0 += VU) {
-    float4 c0[VU][2], c1[VU][2], c2[VU][2], c3[VU][2];
+  float4 c0[2][VU][2], c1[2][VU][2], c2[2][VU][2], c3[2][VU][2];      // [buffer][pair][element]
+  auto issue = [&](int buf, int k0) {
 #pragma unroll
     for (int r = 0; r < VU; ++r) {
       const int p = lane + 32 * (k0 + r);
@@ -204,10 +207,12 @@ __device__ __noinline__ void step_virt_tmem(const int kind, const float *__restr
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const float *rp = row + e * (H / 2);
-        c0[r][e] = ldg4_hint(rp, pol); c1[r][e] = ldg4_hint(rp + H, pol);
-        c2[r][e] = ldg4_hint(rp + 2 * H, pol); c3[r][e] = ldg4_hint(rp + 3 * H, pol);
+        c0[buf][r][e] = ldg4_hint(rp, pol); c1[buf][r][e] = ldg4_hint(rp + H, pol);
+        c2[buf][r][e] = ldg4_hint(rp + 2 * H, pol); c3[buf][r][e] = ldg4_hint(rp + 3 * H, pol);
       }
     }
+  };
+  auto compute = [&](int buf, int k0) {
 #pragma unroll
     for (int r = 0; r < VU; ++r) {
       const int p = lane + 32 * (k0 + r);
@@ -220,15 +225,24 @@ __device__ __noinline__ void step_virt_tmem(const int kind, const float *__restr
         const int sh = j & 31;
         float4 y0, y1;
         if (!right) {              // left half of the codeword: stage M-1 node = f(channel)
-          y0 = f4neg(c0[r][e], c2[r][e]); y1 = f4neg(c1[r][e], c3[r][e]);
+          y0 = f4neg(c0[buf][r][e], c2[buf][r][e]); y1 = f4neg(c1[buf][r][e], c3[buf][r][e]);
         } else {                   // right half: stage M-1 node = g(channel, beta of the left half)
-          y0 = g4neg(c0[r][e], c2[r][e], bw[0] >> sh); y1 = g4neg(c1[r][e], c3[r][e], bw[HW] >> sh);
+          y0 = g4neg(c0[buf][r][e], c2[buf][r][e], bw[0] >> sh); y1 = g4neg(c1[buf][r][e], c3[buf][r][e], bw[HW] >> sh);
         }
         if (!is_g) o[e] = f4(y0, y1);
         else o[e] = g4(y0, y1, bw[gw] >> sh);
       }
       tmem_st8(tm_base + 8 * (k0 + r), o[0], o[1]);
     }
+  };
+  // software pipeline: the loads of round r+1 are in flight while round r is computed (static buffer indices)
+  issue(0, 0);
+#pragma unroll 1
+  for (int k0 = 0; k0 < KMAX; k0 += 2 * VU) {
+    issue(1, k0 + VU);
+    compute(0, k0);
+    if (k0 + 2 * VU < KMAX) issue(0, k0 + 2 * VU);
+    compute(1, k0 + VU);
   }
   tmem_wait_st();
 }
@@ -270,11 +284,11 @@ __device__ __noinline__ void step_glob_tmem(const float *__restrict__ logit, int
 }
 
 // stage TS (tensor memory, lane-private pairs) -> stage TS-1 in shared memory.
-template <int TS, bool IS_G>   // TS = stage held in tensor memory; writes stage TS-1
+template <int TS, bool IS_G, int BOT>   // TS = stage held in tensor memory; writes stage TS-1
 PDEV void step_tmem(float *L, const uint32_t *beta, int stride, int nws, int lane, uint32_t tm_base, int left_word) {
   constexpr int H = 1 << (TS - 1), PQ = H >> 2;        // H outputs per codeword = PQ float4
   constexpr int KMAX = PQ;
-  float *dst = L + (H - 64);
+  float *dst = L + (H - (1 << BOT));
 #pragma unroll 2
   for (int k0 = 0; k0 < KMAX; k0 += 2) {
     Tm8 v0, v1;
@@ -325,6 +339,43 @@ PDEV uint2 bottom64(const float *node, uint32_t fm0, uint32_t fm1) {
 
 // MODE 0: stages 6..M-1 in shared memory (n <= 256).  MODE 1: stage M-1 in tensor memory (n = 512).
 // MODE 2: stage M-1 virtual, stage M-2 in tensor memory (n >= 1024).
+// the 128-leaf subtree below the lane's stage-7 node: both 64-leaf halves in registers (x[64] + the BetaTree levels),
+// so that shared memory only has to hold stage 7 (one more warp per SM) and stage 6 costs no LDS/STS round trip.
+PDEV uint64_t tree64(const float (&x)[64], uint64_t fm) {
+  uint32_t bl = 0, bc = 0;
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t fmc = h ? (uint32_t)(fm >> 32) : (uint32_t)fm;
+    if (fmc == FULLMASK) { bc = 0; continue; }
+    float y[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      y[j] = h ? g_minsum(x[j], x[j + 32], (bl << (31 - j)) & 0x80000000u) : f_minsum(x[j], x[j + 32]);
+    bc = BetaTree<5>::run(y, fmc);
+    if (h == 0) bl = bc;
+  }
+  return (uint64_t)(bl ^ bc) | ((uint64_t)bc << 32);
+}
+PDEV uint4 bottom128(const float *node, uint64_t fm0, uint64_t fm1) {
+  uint64_t bl = 0, bc = 0;
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const uint64_t fmc = h ? fm1 : fm0;
+    if (fmc == ~0ull) { bc = 0; continue; }
+    float x[64];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const float4 a = lds4(node + 4 * q), b = lds4(node + 64 + 4 * q);
+      const float4 o = h ? g4(a, b, (uint32_t)(bl >> (4 * q))) : f4(a, b);
+      x[4 * q] = o.x; x[4 * q + 1] = o.y; x[4 * q + 2] = o.z; x[4 * q + 3] = o.w;
+    }
+    bc = tree64(x, fmc);
+    if (h == 0) bl = bc;
+  }
+  const uint64_t lo = bl ^ bc;
+  return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)bc, (uint32_t)(bc >> 32));
+}
+
 template <int M, int MODE>
 __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ logit, const uint32_t *__restrict__ fmask_g,
                                                      int64_t B, int64_t nbatches, int l2_prefetch, int l2_hints, int dbg,
@@ -332,19 +383,20 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
                                                      const int32_t *__restrict__ info_pos, int k) {
   constexpr bool TM = MODE >= 1, VIRT = MODE == 2;
   constexpr int TS = VIRT ? M - 2 : M - 1;                  // stage held in tensor memory (TM only)
-  static_assert(MODE == 0 ? (M >= 7) : (TS >= 7 && TS <= 9), "sc4: stage 6 must exist in shared memory; a warp reaches 512 TMEM columns");
+  static_assert(MODE == 0 ? (M >= 7) : (TS >= 8 && TS <= 9), "sc4: the bottom stage must exist in shared memory; a warp reaches 512 TMEM columns");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int N = 1 << M, NW = N >> 5, NWS = NW + 1, N64 = N >> 6, TOP = TM ? TS - 1 : M - 1;
+  constexpr int BOT = (M >= 8) ? 7 : 6;                      // stage of the node the per-lane subtree starts from
+  constexpr int WB = 1 << (BOT - 5);                         // 32-bit words per bottom block
+  constexpr int N = 1 << M, NW = N >> 5, NWS = NW + 1, N64 = N >> BOT, TOP = TM ? TS - 1 : M - 1;
   constexpr int TM_COLS_WARP = TM ? (1 << TS) : 32;         // 32 codewords x 2^TS floats / 32 lanes
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const Sc4Layout lay = sc4_layout(M, TOP, nwarps);
-  constexpr int stride = (2 << TOP) - 64 + 4;    // == lay.stride, compile-time so that row offsets fold into immediates
+  const Sc4Layout lay = sc4_layout(M, TOP, BOT, nwarps);
+  constexpr int stride = (2 << TOP) - (1 << BOT) + 4;   // == lay.stride, compile-time so that row offsets fold into immediates
   uint32_t *fmask = reinterpret_cast<uint32_t *>(smem_raw);
   unsigned char *nz = smem_raw + lay.nz_off;    // nz[(N64 >> lv) + (i >> lv)]: node of 2^lv 64-blocks at block i is rate-0
   uint32_t *tm_slot = reinterpret_cast<uint32_t *>(smem_raw + lay.warp_off - 16);
   float *L = reinterpret_cast<float *>(smem_raw + lay.warp_off + (size_t)warp * lay.per_warp);
   uint32_t *beta = reinterpret_cast<uint32_t *>(L + 32 * stride);
-  const int pf_at = (N64 * l2_prefetch) >> 3;   // prefetch point in eighths of the codeword
 
   uint32_t tm_base = 0;
   if (TM) {
@@ -362,7 +414,11 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
     // warp w: TMEM lanes 32(w%4)..+31 (the only ones it can address), column block w/4
     tm_base = *tm_slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TM_COLS_WARP);
   }
-  for (int i = tid; i < N64; i += blockDim.x) nz[N64 + i] = (fmask[2 * i] & fmask[2 * i + 1]) == FULLMASK;
+  for (int i = tid; i < N64; i += blockDim.x) {
+    uint32_t all = FULLMASK;
+    for (int w = 0; w < WB; ++w) all &= fmask[WB * i + w];
+    nz[N64 + i] = all == FULLMASK;
+  }
   __syncthreads();
   if (tid == 0)
     for (int idx = N64 - 1; idx >= 1; --idx) nz[idx] = nz[2 * idx] & nz[2 * idx + 1];
@@ -375,62 +431,71 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
     const int64_t cw0 = batch * 32;
     const int nvalid = (int)((B - cw0) < 32 ? (B - cw0) : 32);
     int i = 0;                                   // current 64-leaf block
-    bool prefetched = !l2_prefetch;
     while (i < N64) {
       // node entered at block i: the root, or the right child whose left sibling just finished
-      const int S = (i == 0) ? M : 6 + (__ffs(i) - 1);
+      const int S = (i == 0) ? M : BOT + (__ffs(i) - 1);
       int s = S;
-      if (!prefetched && i >= pf_at) {           // late in the batch: pull the next batch's rows into the L2
-        prefetched = true;
-        const int64_t nb = batch + wstride;
-        if (nb < nbatches) {
-          const int64_t r0 = nb * 32, r1 = (r0 + 32 < B) ? r0 + 32 : B;
-          prefetch_rows_l2(logit + r0 * (int64_t)N, (size_t)(r1 - r0) * N * 4, lane);
+      if (VIRT && l2_prefetch && ((i + 1) & (N64 / 4 - 1)) == 0) {
+        // the block after this one starts with a pass over the channel rows (this batch's next quarter, or the next
+        // batch's first): ask the L2 for them now, one 64-leaf.. block (several microseconds) ahead of the loads
+        const int64_t pb = (i + 1 < N64) ? batch : batch + wstride;
+        if (pb < nbatches) {
+          const int64_t r = pb * 32 + lane;
+          if (r < B) {
+            const float *rp = logit + r * (int64_t)N;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rp), "r"(N * 4) : "memory");
+          }
         }
       }
-      bool zeroed = nz[(N64 >> (S - 6)) + (i >> (S - 6))] != 0;
+      bool zeroed = nz[(N64 >> (S - BOT)) + (i >> (S - BOT))] != 0;
       if (!zeroed && S < M && !(VIRT && S == M - 1)) {
         // g step into (S, i) from its parent at stage S+1; the left sibling's beta starts at word 2*(i - 2^(S-6))
-        const int left_word = 2 * (i - (1 << (S - 6)));
+        const int left_word = WB * (i - (1 << (S - BOT)));
         if (VIRT && S == M - 2) {
           step_virt_tmem<M>(i < N64 / 2 ? 1 : 3, logit, cw0, nvalid, beta, NWS, lane, tm_base, l2_hints);
         } else if (TM && !VIRT && S == M - 1) {
           step_glob_tmem<M, true>(logit, cw0, nvalid, beta, NWS, lane, tm_base);
         } else if (TM && S == TS - 1) {
-          step_tmem<TS, true>(L, beta, stride, NWS, lane, tm_base, left_word);
+          step_tmem<TS, true, BOT>(L, beta, stride, NWS, lane, tm_base, left_word);
         } else if (!TM && S == M - 1) {
-          step_glob<M, true>(logit, cw0, nvalid, L, beta, stride, NWS, lane);
+          step_glob<M, true, BOT>(logit, cw0, nvalid, L, beta, stride, NWS, lane);
         } else {
-          step_smem_any<TOP - 1, true>(S, L, beta, stride, NWS, lane, left_word);
+          step_smem_any<TOP - 1, true, BOT>(S, L, beta, stride, NWS, lane, left_word);
         }
         __syncwarp();
         SC4_T((VIRT && S == M - 2) ? 0 : 1);
       }
-      while (!zeroed && s > 6) {
-        if (nz[(N64 >> (s - 7)) + (i >> (s - 7))]) { zeroed = true; --s; break; }   // left child is rate-0
+      while (!zeroed && s > BOT) {
+        if (nz[(N64 >> (s - 1 - BOT)) + (i >> (s - 1 - BOT))]) { zeroed = true; --s; break; }   // left child is rate-0
         if (VIRT && s == M) { --s; continue; }                                         // virtual stage: nothing stored
         if (VIRT && s == M - 1) {
           step_virt_tmem<M>(i < N64 / 2 ? 0 : 2, logit, cw0, nvalid, beta, NWS, lane, tm_base, l2_hints);
         } else if (TM && !VIRT && s == M) {
           step_glob_tmem<M, false>(logit, cw0, nvalid, beta, NWS, lane, tm_base);
         } else if (TM && s == TS) {
-          step_tmem<TS, false>(L, beta, stride, NWS, lane, tm_base, 0);
+          step_tmem<TS, false, BOT>(L, beta, stride, NWS, lane, tm_base, 0);
         } else if (!TM && s == M) {
-          step_glob<M, false>(logit, cw0, nvalid, L, beta, stride, NWS, lane);
+          step_glob<M, false, BOT>(logit, cw0, nvalid, L, beta, stride, NWS, lane);
         } else {
-          step_smem_any<TOP - 1, false>(s - 1, L, beta, stride, NWS, lane, 0);
+          step_smem_any<TOP - 1, false, BOT>(s - 1, L, beta, stride, NWS, lane, 0);
         }
         __syncwarp();
         SC4_T((VIRT && s == M - 1) ? 0 : 2);
         --s;
       }
-      const int lv0 = s - 6;                     // the finished node covers 2^lv0 64-blocks starting at i
+      const int lv0 = s - BOT;                   // the finished node covers 2^lv0 bottom blocks starting at i
       if (zeroed) {
-        const int nwd = 2 << lv0;
+        const int nwd = WB << lv0;
         for (int q = lane; q < 32 * nwd; q += 32) {
-          const int c = q >> (lv0 + 1), w = q & (nwd - 1);
-          beta[c * NWS + 2 * i + w] = 0u;
+          const int c = q / nwd, w = q & (nwd - 1);
+          beta[c * NWS + WB * i + w] = 0u;
         }
+      } else if (BOT == 7) {
+        const uint32_t *fmw = fmask + 4 * i;
+        const uint4 b = bottom128(L + lane * stride, (uint64_t)fmw[0] | ((uint64_t)fmw[1] << 32),
+                                  (uint64_t)fmw[2] | ((uint64_t)fmw[3] << 32));
+        uint32_t *bp = beta + lane * NWS + 4 * i;
+        bp[0] = b.x; bp[1] = b.y; bp[2] = b.z; bp[3] = b.w;
       } else {
         const uint2 b = bottom64(L + lane * stride, fmask[2 * i], fmask[2 * i + 1]);
         uint32_t *bp = beta + lane * NWS + 2 * i;
@@ -440,11 +505,11 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
       SC4_T(3);
       {  // merge partial sums upward while the finished node is a right child: [bl ^ br, br] (polar_sc.py:83-89)
         int lv = lv0, a = i;
-        while (lv < M - 6 && ((a >> lv) & 1)) {
-          const int nwd = 2 << lv, left = a - (1 << lv);
+        while (lv < M - BOT && ((a >> lv) & 1)) {
+          const int nwd = WB << lv, left = a - (1 << lv);
           for (int q = lane; q < 32 * nwd; q += 32) {
-            const int c = q >> (lv + 1), w = q & (nwd - 1);
-            beta[c * NWS + 2 * left + w] ^= beta[c * NWS + 2 * a + w];
+            const int c = q / nwd, w = q & (nwd - 1);
+            beta[c * NWS + WB * left + w] ^= beta[c * NWS + WB * a + w];
           }
           __syncwarp();
           a = left; ++lv;
@@ -505,9 +570,9 @@ int launch_sc4_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t 
   if (TM) wmax = 4 * (512 >> TS);               // TMEM columns: 2^TS per warp, 512 per lane quarter
   if (wmax > 8) wmax = 8;
   if (warps <= 0 || warps > wmax) warps = wmax;
-  constexpr int TOP = TM ? TS - 1 : M - 1;
-  while (warps > 1 && sc4_layout(M, TOP, warps).total > (size_t)max_smem) --warps;
-  const Sc4Layout lay = sc4_layout(M, TOP, warps);
+  constexpr int TOP = TM ? TS - 1 : M - 1, BOT = (M >= 8) ? 7 : 6;
+  while (warps > 1 && sc4_layout(M, TOP, BOT, warps).total > (size_t)max_smem) --warps;
+  const Sc4Layout lay = sc4_layout(M, TOP, BOT, warps);
   if (lay.total > (size_t)max_smem) return set_error(POLAR_ENOMEM, "sc: n=%d needs %zu B shared memory per CTA", 1 << M, lay.total);
   auto kern = sc4_kernel<M, MODE>;
   // one persistent CTA per SM.  With tensor memory the CTA takes all 512 columns, so a second CTA must never
@@ -521,7 +586,7 @@ int launch_sc4_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t 
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
   kern<<<(unsigned)grid, warps * 32, smem, st>>>(logit, fmask, B, nbatches, env_int("POLAR_SC4_PREFETCH", 0),
-                                                  env_int("POLAR_SC4_HINTS", 1), env_int("POLAR_SC3_DBG", 0), u_packed, u_info, info_pos, k);
+                                                  env_int("POLAR_SC4_HINTS", 2), env_int("POLAR_SC3_DBG", 0), u_packed, u_info, info_pos, k);
   count_launch();
   POLAR_CHECK_LAUNCH("sc4_kernel");
   return POLAR_OK;
