@@ -320,3 +320,67 @@ def test_on_device_loop_with_process_group_of_one():
     finally:
         dist.destroy_process_group()
     assert np.array_equal(ref[2], got[2]) and np.array_equal(ref[3], got[3])
+
+
+def test_full_size_properties_scl_configs():
+    """BASELINE configs[2] (SCL L=8, n=1024, CRC11, 2^18 codewords) and configs[3] (SCL L=32, n=2048, k=1024) at full
+    list size: (a) split-invariance and determinism of the whole batch; (b) noiseless codewords decode to the transmitted
+    bits with path metric 0; (c) the list decoder is never worse than SC on the same noise and CRC-aided selection is
+    never worse than plain selection; (d) a slice of the full batch is bit-exact against the oracle."""
+    torch, dk, po, co, dev = _env()
+    from my_sn.fec.crc import CRCEncoder
+    # ---- configs[2]
+    n, k, B, L = 1024, 512, 1 << 18, 8
+    fp = golden("frozen_sets")["rm_1024_512"]
+    tables = dk.code_tables(fp, n, dev)
+    chk = CRCEncoder("CRC11", k)
+    gen = CRCEncoder("CRC11", k - chk.crc_length)
+    rows = torch.from_numpy(chk.syndrome_rows(tables.info_pos_np, n).view(np.int32).copy()).to(dev)
+    payload = torch.randint(0, 2, (B, k - gen.crc_length), device=dev, dtype=torch.float32)
+    bits = gen(payload)
+    cw = dk.encode_f32(bits, tables)
+    lg = dk.qpsk_awgn_llr(cw, po.ebnodb2no(3.5, 2, k / n), 777)
+    full = torch.zeros((B, n), dtype=torch.float32, device=dev)
+    full[:, tables.info_pos.long()] = bits
+    tx = dk.pack_bits(full)
+    aided = dk.scl_decode(lg, tables, L, crc_rows=rows, crc_len=chk.crc_length, want_info=False, want_packed=True)["u_packed"]
+    again = dk.scl_decode(lg, tables, L, crc_rows=rows, crc_len=chk.crc_length, want_info=False, want_packed=True)["u_packed"]
+    assert torch.equal(aided, again)
+    parts = torch.cat([dk.scl_decode(lg[a:b], tables, L, crc_rows=rows, crc_len=chk.crc_length, want_info=False,
+                                     want_packed=True)["u_packed"] for a, b in ((0, 3), (3, 70001), (70001, B))])
+    assert torch.equal(parts, aided)
+    plain = dk.scl_decode(lg, tables, L, want_info=False, want_packed=True)["u_packed"]
+    _, sc = dk.sc_decode(lg, tables, want_info=False, want_packed=True)
+
+    def bler(hat):
+        cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+        dk.count_errors_packed(tx, hat, tables.info_mask, n, cnt)
+        return cnt[1].item() / B
+    b_aided, b_plain, b_sc = bler(aided), bler(plain), bler(sc)
+    assert b_aided <= b_plain + 1e-3 and b_plain <= b_sc + 1e-3 and b_aided < 0.9 * b_sc, (b_aided, b_plain, b_sc)
+    sl = slice(B - 48, B)
+    u_ref, pm_ref = co.scl_decode_full(lg[sl].cpu().numpy(), po.frozen_vec(fp, n), L)
+    got = dk.scl_decode(lg[sl], tables, L, want_info=False, want_packed=True, want_pm=True)
+    assert np.array_equal(unpack_words(got["u_packed"].cpu().numpy(), n), u_ref[:, 0])
+    assert np.allclose(got["pm"].cpu().numpy()[:, 0], pm_ref[:, 0], rtol=1e-5, atol=1e-9)
+    assert torch.equal(got["u_packed"], plain[sl])
+    # ---- configs[3]: L = 32, n = 2048
+    n, k, B, L = 2048, 1024, 1 << 13, 32
+    fp = golden("frozen_sets")["rm_2048_1024"]
+    tables = dk.code_tables(fp, n, dev)
+    u, c, lg = dk.awgn_frontend(tables, B, po.ebnodb2no(3.0, 2, k / n), seed=11, want_codeword=True)
+    res = dk.scl_decode(lg, tables, L, want_info=False, want_packed=True, want_pm=True)
+    _, sc = dk.sc_decode(lg, tables, want_info=False, want_packed=True)
+    cnt = torch.zeros(2, dtype=torch.int64, device=dev); cnt2 = torch.zeros(2, dtype=torch.int64, device=dev)
+    dk.count_errors_packed(u, res["u_packed"], tables.info_mask, n, cnt)
+    dk.count_errors_packed(u, sc, tables.info_mask, n, cnt2)
+    assert cnt[1].item() <= cnt2[1].item()
+    pm = res["pm"].cpu().numpy()
+    assert (np.diff(pm, axis=1) >= 0).all()                         # list is sorted by path metric
+    cb = unpack_words(c[:512].cpu().numpy(), n).astype(np.float32)
+    clean = torch.from_numpy((2 * cb - 1) * 40.0).to(dev)            # |LLR| > 30: clipped, penalty log(1+e^-30) per leaf
+    r2 = dk.scl_decode(clean, tables, L, want_info=False, want_packed=True, want_pm=True)
+    assert torch.equal(r2["u_packed"], u[:512])
+    assert np.allclose(r2["pm"].cpu().numpy()[:, 0], n * np.log1p(np.exp(-30.0)), rtol=1e-9)
+    u_ref, pm_ref = co.scl_decode_full(lg[:6].cpu().numpy(), po.frozen_vec(fp, n), L)
+    assert np.array_equal(unpack_words(res["u_packed"][:6].cpu().numpy(), n), u_ref[:, 0])
