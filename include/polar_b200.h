@@ -99,6 +99,17 @@ int polar_encode_packed(const uint32_t *d_u_full_packed, int n, int64_t B, uint3
 int polar_encode_f32(const float *d_u, const int32_t *d_info_rank, int n, int k, int64_t B,
                      float *d_c, uint32_t *d_c_packed_or_null, void *stream);
 
+/* ---- 5G rate matching / rate recovery (TS 38.212 5.4.1) -----------------------------------
+ * polar_gather_cols_f32: out[b, e] = x[b, idx[e]] -- Polar5GEncoder.forward's combined sub-block interleaver +
+ * circular buffer + channel interleaver (my_sn/fec/polar/enc.py:378-381; idx built on the host, enc.py:262-361).
+ * polar_rate_recover_f32: out[b, j] = fill[j], replaced by x[b, src0[j]] when src0[j] >= 0, plus x[b, src1[j]] when
+ * src1[j] >= 0 -- Polar5GDecoder.forward's channel de-interleaver, de-puncturing (fill 0), de-shortening (fill -100),
+ * repetition combining and sub-block de-interleaver in one pass (my_sn/fec/polar/dec.py:600-634). */
+int polar_gather_cols_f32(const float *d_x, const int32_t *d_idx, int n_in, int n_out, int64_t B, float *d_out,
+                          void *stream);
+int polar_rate_recover_f32(const float *d_x, const int32_t *d_src0, const int32_t *d_src1, const float *d_fill,
+                           int n_in, int n_out, int64_t B, float *d_out, void *stream);
+
 /* ---- BPSK/AWGN LLR front end -----------------------------------------------------------------
  * Replaces System_AWGN_model.forward up to the decoder call (z_sys_model/awgn_model.py:33-40):
  * BinarySource -> PolarEncoder -> Mapper (QPSK = BPSK per dimension, amplitude 1/sqrt2) -> AWGN

@@ -161,6 +161,49 @@ def gen_sc_boxplus(fz):
              ebno_db=np.float32(ebno_db))
 
 
+def gen_5g():
+    """5G rate matching (my_sn/fec/polar/enc.py:115-392) and rate recovery (dec.py:539-667) of the reference:
+    index plans, encoded codewords and de-rate-matched decoder inputs for puncturing, shortening and repetition."""
+    from my_sn.fec.polar.enc import Polar5GEncoder
+    from my_sn.fec.polar.dec import Polar5GDecoder
+    cfgs = [(12, 160), (20, 64), (32, 64), (40, 100), (64, 128), (64, 200), (100, 150), (100, 300), (200, 256), (256, 512),
+            (300, 1088), (500, 600), (500, 1024), (700, 1000), (1013, 1088), (57, 70), (33, 45), (150, 400)]
+    out = {"cfgs": np.array(cfgs, dtype=np.int64)}
+    rng = np.random.default_rng(5)
+    for (k, n) in cfgs:
+        enc = Polar5GEncoder(k, n)
+        key = "%d_%d" % (k, n)
+        out["npolar_" + key] = np.int64(enc.n_polar)
+        out["crclen_" + key] = np.int64(enc.enc_crc.crc_length)
+        out["frozen_" + key] = np.asarray(enc._frozen_pos, dtype=np.int64)
+        out["idx_" + key] = np.asarray(enc._ind_rate_matching, dtype=np.int64)
+        u = rng.integers(0, 2, (6, k)).astype(np.float32)
+        out["u_" + key] = u.astype(np.uint8)
+        out["c_" + key] = enc(tc.from_numpy(u)).numpy().astype(np.uint8)
+        dec = Polar5GDecoder(enc, dec_type="SC")
+        grab = {}
+
+        class Grab(tc.nn.Module):
+            def forward(self, x):
+                grab["x"] = x.clone()
+                return tc.zeros([x.shape[0], enc.k_polar])
+        dec._polar_dec = Grab()
+        llr = (rng.standard_normal((4, n)) * 5).astype(np.float32)
+        dec(tc.from_numpy(llr))
+        out["llr_" + key] = llr
+        out["dem_" + key] = grab["x"].numpy().astype(np.float32)
+        print("5g k=%d n=%d: n_polar=%d crc=%d" % (k, n, enc.n_polar, enc.enc_crc.crc_length))
+    # downlink plan (forward raises in the reference; the tables are still built)
+    for (k, n) in [(30, 108), (140, 576)]:
+        enc = Polar5GEncoder(k, n, channel_type="downlink")
+        key = "dl_%d_%d" % (k, n)
+        out["npolar_" + key] = np.int64(enc.n_polar)
+        out["frozen_" + key] = np.asarray(enc._frozen_pos, dtype=np.int64)
+        out["idx_" + key] = np.asarray(enc._ind_rate_matching, dtype=np.int64)
+        out["iil_" + key] = np.asarray(enc._ind_input_int, dtype=np.int64)
+    save("nr5g", **out)
+
+
 def packbits(a):
     return np.packbits(a.astype(np.uint8), axis=-1, bitorder="little")
 
@@ -328,7 +371,7 @@ def gen_readme_kat(fz):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["frozen", "enc", "sc", "scbp", "scl", "crc", "frontend", "readme"]
+    which = sys.argv[1:] or ["frozen", "enc", "sc", "scbp", "nr5g", "scl", "crc", "frontend", "readme"]
     fz = gen_frozen() if "frozen" in which else dict(np.load(os.path.join(OUT, "frozen_sets.npz")))
     if "enc" in which:
         gen_enc(fz)
@@ -342,5 +385,7 @@ if __name__ == "__main__":
         gen_sc(fz)
     if "scbp" in which:
         gen_sc_boxplus(fz)
+    if "nr5g" in which:
+        gen_5g()
     if "scl" in which:
         gen_scl(fz)

@@ -178,3 +178,67 @@ extern "C" int polar_unpack_info_f32(const uint32_t *d_packed, const int32_t *d_
   POLAR_CHECK_LAUNCH("unpack_info");
   return POLAR_OK;
 }
+
+
+// ---- 5G rate matching / recovery -------------------------------------------------------------
+// Polar5GEncoder.forward (my_sn/fec/polar/enc.py:378-381): sub-block interleaver, circular-buffer selection and channel
+// interleaver are ONE gather c_matched[b, e] = c[b, idx[e]].  Polar5GDecoder.forward (my_sn/fec/polar/dec.py:607-634):
+// channel de-interleaver, de-puncturing (logit 0), de-shortening (logit -100), repetition combining (sum) and the
+// sub-block de-interleaver are ONE pass out[b, j] = fill[j] + x[b, src0[j]] + x[b, src1[j]] (negative index = absent).
+namespace polar {
+__global__ void __launch_bounds__(256) gather_cols_kernel(const float *__restrict__ x, const int32_t *__restrict__ idx, int n_in,
+                                                          int n_out, int64_t B, float *__restrict__ out) {
+  const int64_t total = B * (int64_t)n_out;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = t / n_out;
+    const int e = (int)(t - b * n_out);
+    out[t] = __ldg(x + b * n_in + __ldg(idx + e));
+  }
+}
+__global__ void __launch_bounds__(256) rate_recover_kernel(const float *__restrict__ x, const int32_t *__restrict__ src0,
+                                                           const int32_t *__restrict__ src1, const float *__restrict__ fill,
+                                                           int n_in, int n_out, int64_t B, float *__restrict__ out) {
+  const int64_t total = B * (int64_t)n_out;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = t / n_out;
+    const int j = (int)(t - b * n_out);
+    const int s0 = __ldg(src0 + j), s1 = __ldg(src1 + j);
+    float v = __ldg(fill + j);
+    if (s0 >= 0) v = __ldg(x + b * n_in + s0);          // received position (fill is 0 there)
+    if (s1 >= 0) v = v + __ldg(x + b * n_in + s1);      // repetition: llr_1 + llr_3 (dec.py:617-620)
+    out[t] = v;
+  }
+}
+}  // namespace polar
+
+static unsigned perm_grid(int64_t total) {
+  int64_t g = (total + 255) / 256;
+  const int64_t cap = (int64_t)polar::device_sm_count() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+extern "C" int polar_gather_cols_f32(const float *d_x, const int32_t *d_idx, int n_in, int n_out, int64_t B, float *d_out,
+                                     void *stream) {
+  using namespace polar;
+  if (n_in < 1 || n_out < 1 || B < 0) return set_error(POLAR_EINVAL, "gather: bad sizes");
+  if (B == 0) return POLAR_OK;
+  if (!d_x || !d_idx || !d_out) return set_error(POLAR_EINVAL, "gather: null pointer");
+  gather_cols_kernel<<<perm_grid(B * n_out), 256, 0, (cudaStream_t)stream>>>(d_x, d_idx, n_in, n_out, B, d_out);
+  count_launch();
+  POLAR_CHECK_LAUNCH("gather_cols");
+  return POLAR_OK;
+}
+
+extern "C" int polar_rate_recover_f32(const float *d_x, const int32_t *d_src0, const int32_t *d_src1, const float *d_fill,
+                                      int n_in, int n_out, int64_t B, float *d_out, void *stream) {
+  using namespace polar;
+  if (n_in < 1 || n_out < 1 || B < 0) return set_error(POLAR_EINVAL, "rate_recover: bad sizes");
+  if (B == 0) return POLAR_OK;
+  if (!d_x || !d_src0 || !d_src1 || !d_fill || !d_out) return set_error(POLAR_EINVAL, "rate_recover: null pointer");
+  rate_recover_kernel<<<perm_grid(B * n_out), 256, 0, (cudaStream_t)stream>>>(d_x, d_src0, d_src1, d_fill, n_in, n_out, B, d_out);
+  count_launch();
+  POLAR_CHECK_LAUNCH("rate_recover");
+  return POLAR_OK;
+}

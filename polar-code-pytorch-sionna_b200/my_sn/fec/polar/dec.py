@@ -134,3 +134,88 @@ class SCL_Dec(nn.Module):
     if self._return_crc_status:
       raise Exception('not implement...')                              # dec.py:534-535
     return out if inputs.is_cuda else out.to(inputs.device)
+
+
+class Polar5GDecoder(nn.Module):
+  """Rate recovery + polar decoding + CRC removal for codewords of `Polar5GEncoder` (my_sn/fec/polar/dec.py:539-667,
+  SURVEY 8f row N3).  Channel de-interleaver, de-puncturing (logit 0), de-shortening (logit -100), repetition combining
+  and the sub-block de-interleaver are folded into one index plan applied by `polar_rate_recover_f32`; the decoder is the
+  my_sn `SC_Dec` (boxplus SC) or the CRC-aided `SCL_Dec`.  `dec_type="hybSCL"` runs the CRC-aided list decoder (the
+  reference's hybrid branch cannot be constructed); `return_crc_status=True` works here (the reference stops in a
+  stray breakpoint, dec.py:661)."""
+
+  def __init__(self, enc_polar, dec_type="SC", list_size=8, return_crc_status=False, output_dtype=tc.float32):
+    super().__init__()
+    self._output_dtype = output_dtype
+    self._n_target = enc_polar.n_target; self._k_target = enc_polar.k_target
+    self._n_polar = enc_polar.n_polar; self._k_polar = enc_polar.k_polar
+    self._k_crc = enc_polar.enc_crc.crc_length
+    self._bil = enc_polar._channel_type == "uplink"
+    self._iil = False
+    self._llr_max = 100
+    self._enc_polar = enc_polar; self._dec_type = dec_type
+    self._init_interleavers()
+    if dec_type == "SC":
+      print("Warning: CRC cant be used with SC dec and. Please use SCL dec.")
+      self._polar_dec = SC_Dec(enc_polar._frozen_pos, self._n_polar, device=enc_polar.device)
+    elif dec_type in ("SCL", "hybSCL"):
+      self._polar_dec = SCL_Dec(enc_polar._frozen_pos, self._n_polar, crc_degree=enc_polar.enc_crc.crc_degree,
+                                list_size=list_size, device=enc_polar.device)
+    else:
+      raise ValueError("Unknown value for dec_type.")
+    assert isinstance(return_crc_status, bool), "return_crc_status must be bool."
+    self._return_crc_status = return_crc_status
+    if return_crc_status:
+      self._dec_crc = self._polar_dec._crc_decoder if dec_type in ("SCL", "hybSCL") else CRCDecoder(enc_polar.enc_crc)
+    self._plan_dev = {}
+
+  def _init_interleavers(self):
+    """Inverse interleaver patterns (dec.py:584-598) and the fused rate-recovery plan: for polar position j,
+    out[j] = fill[j], or x[src0[j]] (+ x[src1[j]] under repetition)."""
+    n, e, enc = self._n_polar, self._n_target, self._enc_polar
+    self.ind_ch_int_inv = np.argsort(enc.channel_interleaver(np.arange(e)))
+    self.ind_sub_int_inv = np.argsort(enc.subblock_interleaving(np.arange(n)))
+    self.ind_iil_inv = None
+    deint = self.ind_ch_int_inv if self._bil else np.arange(e)                 # de-interleaved position -> received position
+    src0 = np.full(n, -1, dtype=np.int64); src1 = np.full(n, -1, dtype=np.int64); fill = np.zeros(n, dtype=np.float32)
+    p = np.arange(n)
+    if e >= n:                                                                 # repetition: first E-N positions seen twice
+      src0[:] = deint[p]
+      rep = p[: e - n]
+      src1[rep] = deint[n + rep]
+    elif self._k_polar / e <= 7 / 16:                                          # puncturing: first N-E positions erased
+      src0[n - e:] = deint[p[n - e:] - (n - e)]
+    else:                                                                      # shortening: last N-E positions known zeros
+      src0[:e] = deint[p[:e]]
+      fill[e:] = -float(self._llr_max)                                         # logits: bit 0 with certainty
+    inv = self.ind_sub_int_inv
+    self._plan = (src0[inv].astype(np.int32), src1[inv].astype(np.int32), fill[inv].copy())
+
+  def rate_recover(self, inputs):
+    """[B, n_target] channel logits -> [B, n_polar] decoder logits (dec.py:607-634), on the GPU."""
+    dev = inputs.device if inputs.is_cuda else dk.cuda_device(self._enc_polar.device)
+    plan = self._plan_dev.get(str(dev))
+    if plan is None:
+      plan = self._plan_dev[str(dev)] = tuple(tc.from_numpy(a).to(dev) for a in self._plan)
+    return dk.rate_recover(inputs.to(device=dev, dtype=tc.float32).reshape(-1, self._n_target), *plan)
+
+  def forward(self, inputs):
+    inputs = inputs.to(tc.float32)
+    input_shape = inputs.shape
+    assert len(input_shape) > 1
+    llr_dec = self.rate_recover(inputs)
+    u_hat_crc = self._polar_dec(llr_dec)
+    if self._return_crc_status:
+      u_hat, crc_status = self._dec_crc(u_hat_crc)
+    else:
+      u_hat = u_hat_crc[:, :-self._k_crc]
+    output_shape = [*input_shape]
+    output_shape[-1] = self._k_target
+    output_shape[0] = -1
+    u_hat = u_hat.reshape(output_shape).to(dtype=self._output_dtype)
+    u_hat = u_hat if inputs.is_cuda else u_hat.to(inputs.device)
+    if self._return_crc_status:
+      output_shape.pop()
+      crc_status = crc_status.reshape(output_shape).to(dtype=self._output_dtype)
+      return u_hat, (crc_status if inputs.is_cuda else crc_status.to(inputs.device))
+    return u_hat

@@ -51,6 +51,8 @@ _SIGNATURES = {
   "polar_scl_decode": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
   "polar_encode_packed": (_i32, [_vp, _i32, _i64, _vp, _vp]),
   "polar_encode_f32": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp]),
+  "polar_gather_cols_f32": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp]),
+  "polar_rate_recover_f32": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp]),
   "polar_awgn_frontend": (_i32, [_u64, _u64, _f32, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
   "polar_qpsk_awgn_llr": (_i32, [_u64, _u64, _f32, _vp, _i32, _i64, _vp, _vp]),
   "polar_count_errors_packed": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
@@ -300,6 +302,27 @@ def count_errors_packed(a, b, mask, n, counters):
   with tc.cuda.device(dev):
     check(lib().polar_count_errors_packed(ptr(a.contiguous()), ptr(b.contiguous()), ptr(mask), int(n), a.shape[0],
                                           ptr(counters), stream_ptr(dev)))
+
+
+def gather_cols(x, idx):
+  """polar_gather_cols_f32: out[b, e] = x[b, idx[e]] (idx int32 device tensor)."""
+  dev = x.device
+  x2 = x.to(tc.float32).reshape(-1, x.shape[-1]).contiguous()
+  out = tc.empty((x2.shape[0], idx.shape[0]), dtype=tc.float32, device=dev)
+  with tc.cuda.device(dev):
+    check(lib().polar_gather_cols_f32(ptr(x2), ptr(idx), x2.shape[1], idx.shape[0], x2.shape[0], ptr(out), stream_ptr(dev)))
+  return out
+
+
+def rate_recover(x, src0, src1, fill):
+  """polar_rate_recover_f32: out[b, j] = (src0[j] >= 0 ? x[b, src0[j]] : fill[j]) + (src1[j] >= 0 ? x[b, src1[j]] : 0)."""
+  dev = x.device
+  x2 = x.to(tc.float32).reshape(-1, x.shape[-1]).contiguous()
+  out = tc.empty((x2.shape[0], src0.shape[0]), dtype=tc.float32, device=dev)
+  with tc.cuda.device(dev):
+    check(lib().polar_rate_recover_f32(ptr(x2), ptr(src0), ptr(src1), ptr(fill), x2.shape[1], src0.shape[0], x2.shape[0],
+                                       ptr(out), stream_ptr(dev)))
+  return out
 
 
 def mc_control(delta, state, target_bit_errs, target_block_errs, max_mc_iter):

@@ -178,3 +178,41 @@ def test_register_subtree_decoder_on_host():
                            "-L" + os.path.join(ROOT, "oracle"), "-lpolar_oracle",
                            "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-lpthread"])
     assert subprocess.run([exe], capture_output=True, text=True).stdout.strip().endswith("bad=0")
+
+
+def test_5g_rate_matching_plans_match_reference():
+    """SURVEY 8f N3 (host side): mother-code length, CRC choice, frozen set and the combined rate-matching gather index of
+    Polar5GEncoder for puncturing / shortening / repetition configs, and the interleavers, against the reference's tables."""
+    import numpy as np
+    from util import golden
+    from my_sn.fec.polar.enc import Polar5GEncoder
+    from my_sn.fec.polar.dec import Polar5GDecoder
+    g = golden("nr5g")
+    for k, n in g["cfgs"]:
+        key = "%d_%d" % (k, n)
+        enc = Polar5GEncoder(int(k), int(n))
+        assert enc.n_polar == int(g["npolar_" + key]) and enc.enc_crc.crc_length == int(g["crclen_" + key]), key
+        assert np.array_equal(np.asarray(enc._frozen_pos), g["frozen_" + key]), key
+        assert np.array_equal(enc._ind_rate_matching, g["idx_" + key]), key
+        assert enc.k == k and enc.n == n and enc.k_polar == k + enc.enc_crc.crc_length
+        # the fused rate-recovery plan reproduces the reference's de-rate-matched decoder input on the host
+        dec = Polar5GDecoder(enc, dec_type="SC")               # construction is host-only
+        s0, s1, fill = dec._plan
+        llr = g["llr_" + key]
+        out = np.where(s0 >= 0, llr[:, np.maximum(s0, 0)], fill[None, :]).astype(np.float32)
+        out = out + np.where(s1 >= 0, llr[:, np.maximum(s1, 0)], np.float32(0)).astype(np.float32)
+        assert np.array_equal(out, g["dem_" + key]), key
+    for key in ("dl_30_108", "dl_140_576"):
+        k, n = (int(v) for v in key.split("_")[1:])
+        enc = Polar5GEncoder(k, n, channel_type="downlink")
+        assert enc.n_polar == int(g["npolar_" + key])
+        assert np.array_equal(np.asarray(enc._frozen_pos), g["frozen_" + key])
+        assert np.array_equal(enc._ind_rate_matching, g["idx_" + key])
+        assert np.array_equal(enc._ind_input_int, g["iil_" + key])
+    import pytest
+    with pytest.raises(ValueError):
+        Polar5GEncoder(8, 64)
+    with pytest.raises(AssertionError):
+        Polar5GEncoder(100, 50)
+    with pytest.raises(AssertionError):
+        Polar5GEncoder(200, 400, channel_type="downlink")
