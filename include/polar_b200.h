@@ -88,6 +88,16 @@ int polar_scl_decode(const float *d_logit, const uint32_t *d_frozen_mask, int n,
                      const uint32_t *d_crc_rows, int crc_len,
                      void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* Same calls with the exact boxplus check-node update in fp64 (my_sn/fec/polar/dec.py:331-340): the list decoder of the
+ * Sionna-style SCL_Dec with leaf-level path-metric updates (its use_fast_scl=False arithmetic).
+ * The workspace size is the same function of (n, L, B). */
+size_t polar_scl_boxplus_workspace_bytes(int n, int L, int64_t B);
+int polar_scl_decode_boxplus(const float *d_logit, const uint32_t *d_frozen_mask, int n, int L, int64_t B,
+                             uint32_t *d_best_packed, float *d_u_info_f32, const int32_t *d_info_pos, int k,
+                             double *d_pm_sorted, uint32_t *d_list_packed,
+                             const uint32_t *d_crc_rows, int crc_len,
+                             void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* ---- encoder -----------------------------------------------------------------------------
  * polar_encode_packed: x = u.G over GF(2) on bit-packed rows (XOR butterfly; the transform of
  * my_sn/fec/polar/enc.py:85-96 == (c @ G) % 2 of x_run_sn_polar/polar/enc.py:42).

@@ -161,6 +161,26 @@ def gen_sc_boxplus(fz):
              ebno_db=np.float32(ebno_db))
 
 
+def gen_scl_boxplus(fz):
+    """SURVEY 8f N2 (list decoder): the reference's my_sn SCL_Dec (exact boxplus, numpy float64) with use_fast_scl False
+    (leaf-level path metrics = the arithmetic of polar_scl_decode_boxplus) and True (its default node shortcuts)."""
+    from my_sn.fec.polar.dec import SCL_Dec as MySCL
+    for (n, k, L, bs, ebno_db, crc) in ((64, 32, 8, 300, 2.0, None), (128, 64, 4, 200, 2.0, None), (256, 128, 8, 60, 2.5, "CRC11")):
+        fp = fz["rm_%d_%d" % (n, k)]
+        G = tc.from_numpy(po.arikan_G(n))
+        set_seed(1200 + n)
+        bits, cw, llr = ref_logits(n, k, fp, G, bs, ebno_db)
+        res = {}
+        for fast in (False, True):
+            dec = MySCL(fp, n, list_size=L, crc_degree=crc, use_fast_scl=fast)
+            res[fast] = dec(tc.from_numpy(llr)).numpy().astype(np.uint8)
+        same = np.mean(np.all(res[False] == res[True], axis=1))
+        print("scl-boxplus n=%d L=%d crc=%s: BLER slow %.4f fast %.4f, identical codewords %.4f" %
+              (n, L, crc, np.mean(np.any(res[False] != bits, axis=1)), np.mean(np.any(res[True] != bits, axis=1)), same))
+        save("sclbp_rm_%d_%d_L%d" % (n, k, L), logits=llr, frozen_pos=fp, u_hat=res[False], u_hat_fast=res[True],
+             bits=bits.astype(np.uint8), crc_degree=np.array(crc if crc else ""), list_size=np.int64(L))
+
+
 def gen_5g():
     """5G rate matching (my_sn/fec/polar/enc.py:115-392) and rate recovery (dec.py:539-667) of the reference:
     index plans, encoded codewords and de-rate-matched decoder inputs for puncturing, shortening and repetition."""
@@ -371,7 +391,7 @@ def gen_readme_kat(fz):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["frozen", "enc", "sc", "scbp", "nr5g", "scl", "crc", "frontend", "readme"]
+    which = sys.argv[1:] or ["frozen", "enc", "sc", "scbp", "nr5g", "sclbp", "scl", "crc", "frontend", "readme"]
     fz = gen_frozen() if "frozen" in which else dict(np.load(os.path.join(OUT, "frozen_sets.npz")))
     if "enc" in which:
         gen_enc(fz)
@@ -387,5 +407,7 @@ if __name__ == "__main__":
         gen_sc_boxplus(fz)
     if "nr5g" in which:
         gen_5g()
+    if "sclbp" in which:
+        gen_scl_boxplus(fz)
     if "scl" in which:
         gen_scl(fz)

@@ -27,11 +27,20 @@ namespace polar {
 
 constexpr double kLlrMaxD = 30.0;
 
+#if defined(POLAR_F_BOXPLUS)
+// exact boxplus of the Sionna-style list decoder (my_sn/fec/polar/dec.py:331-340, numpy float64): clip to +-30,
+// ln(1+e^(x+y)) - ln(e^x+e^y).  Selected by polar_bp_wrap.cu (namespace polar_bp, entry point polar_scl_decode_boxplus).
+__device__ __forceinline__ double f_minsum_d(double a, double b) {
+  const double x = fmax(fmin(a, 30.0), -30.0), y = fmax(fmin(b, 30.0), -30.0);
+  return log(1.0 + exp(x + y)) - log(exp(x) + exp(y));
+}
+#else
 __device__ __forceinline__ double f_minsum_d(double a, double b) {   // polar_scl.py:93-106
   const double mag = fmin(fmin(fabs(a), fabs(b)), kLlrMaxD);
   const unsigned long long sgn = (unsigned long long)(__double_as_longlong(a) ^ __double_as_longlong(b)) & 0x8000000000000000ull;
   return __longlong_as_double((long long)((unsigned long long)__double_as_longlong(mag) | sgn));
 }
+#endif
 __device__ __forceinline__ double g_minsum_d(double a, double b, unsigned u) {   // polar_scl.py:107-108
   const unsigned long long sm = (unsigned long long)(u & 1u) << 63;
   return __longlong_as_double((long long)((unsigned long long)__double_as_longlong(a) ^ sm)) + b;

@@ -50,10 +50,19 @@ class SC_Dec(nn.Module):
 
 
 class SCL_Dec(nn.Module):
+  """Sionna-style list decoder (my_sn/fec/polar/dec.py:158-537) with CRC-aided selection (:507-527).
+  cn_type="boxplus" (default, the reference's arithmetic): exact boxplus f in fp64 with leaf-level path-metric updates,
+  i.e. the reference with use_fast_scl=False; its default rate-0/REP node shortcuts only change how the same penalties
+  are accumulated, so `use_fast_scl` is accepted and both settings run this kernel (statistical parity).
+  cn_type="minsum": the x_run min-sum list kernel under the same CRC-aided selection -- the composed oracle of
+  BASELINE config 3, bit-exact against `tests/golden/sclcrc_*`."""
+
   def __init__(self, frozen_pos, n, list_size=8, crc_degree=None, use_hybrid_sc=False, use_fast_scl=True,
-               return_crc_status=False, output_dtype=tc.float32, device='cpu'):
+               return_crc_status=False, output_dtype=tc.float32, device='cpu', cn_type="boxplus"):
     super().__init__()
     self.device = device
+    assert cn_type in ("boxplus", "minsum"), "cn_type must be 'boxplus' or 'minsum'."
+    self._boxplus = cn_type == "boxplus"
     if output_dtype not in (tc.float16, tc.float32, tc.float64):
       raise ValueError('output_dtype must be {tf.float16, tf.float32, tf.float64}.')
     self.output_dtype = output_dtype
@@ -111,7 +120,7 @@ class SCL_Dec(nn.Module):
     """Device fast path of the on-device Monte-Carlo loop: bit-packed decisions of the (CRC-)selected path."""
     rows, ln = self._rows_on(tables.dev)
     return dk.scl_decode(logits, tables, self._list_size, crc_rows=rows, crc_len=ln, want_info=False,
-                         want_packed=True)["u_packed"]
+                         want_packed=True, boxplus=self._boxplus)["u_packed"]
 
   def forward(self, inputs):
     assert inputs.dtype == self.output_dtype, "Invalid input dtype."
@@ -125,7 +134,8 @@ class SCL_Dec(nn.Module):
       if rows is None:
         rows = self._crc_rows[str(dev)] = tc.from_numpy(self._crc_rows_np.view(np.int32).copy()).to(dev)
       ln = self._k_crc
-    res = dk.scl_decode(inputs, tables, self._list_size, crc_rows=rows, crc_len=ln, want_info=True, want_pm=True)
+    res = dk.scl_decode(inputs, tables, self._list_size, crc_rows=rows, crc_len=ln, want_info=True, want_pm=True,
+                        boxplus=self._boxplus)
     self.msg_pm = res["pm"]
     output_shape = list(inputs.shape)
     output_shape[-1] = self.k

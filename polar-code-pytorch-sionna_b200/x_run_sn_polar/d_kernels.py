@@ -49,6 +49,8 @@ _SIGNATURES = {
   "polar_sc_decode_boxplus_f32": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _i32, _vp]),
   "polar_scl_workspace_bytes": (_sz, [_i32, _i32, _i64]),
   "polar_scl_decode": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
+  "polar_scl_boxplus_workspace_bytes": (_sz, [_i32, _i32, _i64]),
+  "polar_scl_decode_boxplus": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
   "polar_encode_packed": (_i32, [_vp, _i32, _i64, _vp, _vp]),
   "polar_encode_f32": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp]),
   "polar_gather_cols_f32": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp]),
@@ -198,8 +200,9 @@ _WS_CACHE = {}
 
 
 def scl_decode(logits, tables, list_size, crc_rows=None, crc_len=0, want_info=True, want_packed=False,
-               want_pm=False, want_list=False):
-  """polar_scl_decode -> dict(u_info, u_packed, pm [B,L] fp64, list [B,L,words] int32)."""
+               want_pm=False, want_list=False, boxplus=False):
+  """polar_scl_decode (min-sum f) or polar_scl_decode_boxplus (exact boxplus f, my_sn SCL_Dec)
+  -> dict(u_info, u_packed, pm [B,L] fp64, list [B,L,words] int32)."""
   dev = tables.dev
   x = _prep_logits(logits, tables.n, dev)
   B, n, L = x.shape[0], tables.n, int(list_size)
@@ -213,13 +216,15 @@ def scl_decode(logits, tables, list_size, crc_rows=None, crc_len=0, want_info=Tr
   if want_list:
     out["list"] = tc.empty((B, L, words(n)), dtype=tc.int32, device=dev)
   with tc.cuda.device(dev):
-    need = int(lib().polar_scl_workspace_bytes(n, L, B)) if B > 0 else 0
+    fn_ws = lib().polar_scl_boxplus_workspace_bytes if boxplus else lib().polar_scl_workspace_bytes
+    fn_dec = lib().polar_scl_decode_boxplus if boxplus else lib().polar_scl_decode
+    need = int(fn_ws(n, L, B)) if B > 0 else 0
     ws = None
     if need:
       ws = _WS_CACHE.get(str(dev))
       if ws is None or ws.numel() < need:
         ws = _WS_CACHE[str(dev)] = tc.empty(need + 256, dtype=tc.uint8, device=dev)
-    check(lib().polar_scl_decode(ptr(x), ptr(tables.frozen_mask), n, L, B, ptr(out["u_packed"]), ptr(out["u_info"]),
+    check(fn_dec(ptr(x), ptr(tables.frozen_mask), n, L, B, ptr(out["u_packed"]), ptr(out["u_info"]),
                                  ptr(tables.info_pos), tables.k, ptr(out["pm"]), ptr(out["list"]),
                                  ptr(crc_rows), int(crc_len), ptr(ws), need, stream_ptr(dev)))
   return out

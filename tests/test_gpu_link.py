@@ -95,7 +95,7 @@ def test_crc_aided_scl_matches_composed_reference(name):
     from my_sn.fec.polar.dec import SCL_Dec
     d = golden(name)
     n = d["logits"].shape[1]
-    dec = SCL_Dec(d["frozen_pos"], n, list_size=8, crc_degree=str(d["crc_degree"]))
+    dec = SCL_Dec(d["frozen_pos"], n, list_size=8, crc_degree=str(d["crc_degree"]), cn_type="minsum")
     out = dec(torch.from_numpy(d["logits"]).to(dev)).cpu().numpy().astype(np.uint8)
     rb = d["robust"]
     assert np.array_equal(out[rb], d["u_sel"][rb])
@@ -121,7 +121,7 @@ def test_crc_aided_scl_matches_oracle_random_and_beats_plain_scl():
     u_b, pm_b = po.scl_decode_full(logits[:600], po.frozen_vec(fp, n), L, use_log1p=True)   # conditioning probe
     sel_b, _ = po.scl_crc_select(u_b, pm_b, fp, n, deg)
     x = torch.from_numpy(logits).to(dev)
-    got = SCL_Dec(fp, n, L, crc_degree=deg)(x).cpu().numpy()
+    got = SCL_Dec(fp, n, L, crc_degree=deg, cn_type="minsum")(x).cpu().numpy()
     diff = np.any(got != sel, axis=1)
     probe = np.any(sel_b != sel[:600], axis=1)
     # decisions agree everywhere except (at most) on ill-conditioned codewords, whose rate the two oracle variants bound

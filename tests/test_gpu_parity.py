@@ -319,3 +319,23 @@ def test_boxplus_sc_all_mappings_vs_restatement(n, B):
     ref = po.sc_decode_boxplus_full(logits, po.frozen_vec(fp, n))[:, po.info_positions(fp, n)]
     got = BoxplusSC(fp, n)(torch.from_numpy(logits).cuda()).cpu().numpy().astype(np.uint8)
     assert np.mean(np.all(got == ref, axis=1)) >= 0.98
+
+
+@pytest.mark.parametrize("name", golden_names("sclbp_"))
+def test_boxplus_scl_matches_reference_statistically(name):
+    """SURVEY 8f N2 (list decoder): my_sn SCL_Dec (exact boxplus f in fp64, polar_scl_decode_boxplus, optional CRC-aided
+    selection) against the reference's my_sn/fec/polar/dec.py::SCL_Dec decisions -- both with its node shortcuts
+    (use_fast_scl=True) and without.  CUDA exp/log are not numpy's, so the bar is statistical: >= 98 % identical codewords."""
+    import torch
+    from my_sn.fec.polar.dec import SCL_Dec
+    d = golden(name)
+    n = d["logits"].shape[1]
+    crc = str(d["crc_degree"]) or None
+    dec = SCL_Dec(d["frozen_pos"], n, list_size=int(d["list_size"]), crc_degree=crc)
+    got = dec(torch.from_numpy(d["logits"]).cuda()).cpu().numpy().astype(np.uint8)
+    assert np.mean(np.all(got == d["u_hat"], axis=1)) >= 0.98
+    assert np.mean(np.all(got == d["u_hat_fast"], axis=1)) >= 0.98
+    ms = SCL_Dec(d["frozen_pos"], n, list_size=int(d["list_size"]), crc_degree=crc, cn_type="minsum")
+    got_ms = ms(torch.from_numpy(d["logits"]).cuda()).cpu().numpy().astype(np.uint8)
+    bler = lambda u: np.any(u != d["bits"], axis=1).mean()
+    assert bler(got) <= bler(got_ms) + 3 * np.sqrt(0.25 / got.shape[0])
