@@ -61,6 +61,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.windows = []          # [t0, t1] intervals (perf_counter) of the timed regions; only those samples count
 
     def start(self):
         try:
@@ -74,7 +75,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def stop(self):
         if not self.proc:
@@ -84,16 +88,18 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        inside = [r for (t, r) in self.rows if any(a - 0.05 <= t <= b + 0.15 for a, b in self.windows)]
+        rows = inside if inside else [r for (_, r) in self.rows]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for i, nm in enumerate(names):
                 if len(r) > 4 + i and r[4 + i].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_regions": len(inside)}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -200,21 +206,22 @@ def main():
     def sc_step():
         dk.check(lib.polar_sc_decode_f32(dk.ptr(logits), dk.ptr(tables.frozen_mask), n, B, dk.ptr(u_hat), None, None, 0, stream))
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                      # runs through the SC and the SCL timed regions (>= 0.5 s under load)
     for _ in range(args.warmup):
         sc_step()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = dk.launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
     t_all0.record()
     for a, b in evs:
         a.record(); sc_step(); b.record()
     t_all1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    sampler.mark(w0, time.perf_counter())
     launches = dk.launch_count() - launches0
     total_ms = max_over_ranks(t_all0.elapsed_time(t_all1))
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))      # one launch per step: the SC kernel itself
@@ -290,11 +297,13 @@ def main():
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = dk.launch_count()
+        w0 = time.perf_counter()
         a.record()
         for _ in range(scl_steps):
             scl_step()
         b.record()
         barrier()
+        sampler.mark(w0, time.perf_counter())
         launches += dk.launch_count() - l0
         scl_ms = max_over_ranks(a.elapsed_time(b) / scl_steps)
         scl_cws = world * Bs / (scl_ms * 1e-3)
@@ -330,11 +339,12 @@ def main():
                           "d2h_bytes_per_step": Bs * nw * 4, "ms_per_step": ms,
                           "matches_device_path": bool(torch.equal(h_best[:2048], best[:2048].cpu()))}
         if rank == 0 and not args.skip_cpu:
-            smp = 4096
+            smp = 16384
             rate, thr, cnt_cw = cpu_oracle_rate("scl", lg[:smp].cpu().numpy(), po.frozen_vec(fp, n), SCL_L)
             scl["cpu_baseline"] = {"value": rate * k / 1e9, "unit": "Gbit/s", "codewords_per_s": rate, "cores": thr, "kind": "port",
                                    "sample": "first %d codewords of the GPU batch, C restatement (oracle/polar_oracle.c)" % cnt_cw}
 
+    clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -344,7 +354,7 @@ def main():
     achieved = B * bytes_per_cw / (kern_ms * 1e-3) / 1e9
     cpu = None
     if not args.skip_cpu:
-        smp = 1 << 18
+        smp = min(B, 1 << 20)
         rate, thr, cnt_cw = cpu_oracle_rate("sc", logits[:smp].cpu().numpy(), po.frozen_vec(fp, n))
         cpu = {"value": rate * k / 1e9, "unit": "Gbit/s", "codewords_per_s": rate, "cores": thr, "kind": "port",
                "sample": "first %d codewords of the GPU batch, C restatement of the reference (oracle/polar_oracle.c); "
