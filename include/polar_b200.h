@@ -137,6 +137,16 @@ int polar_awgn_frontend(uint64_t seed, uint64_t offset, float no, const uint32_t
 int polar_qpsk_awgn_llr(uint64_t seed, uint64_t offset, float no, const float *d_c /*[B,n] 0/1*/,
                         int n, int64_t B, float *d_logit_out, void *stream);
 
+/* Binary erasure channel with LLR output (my_sn/trans/channel/discrete_channel.py:79-107 with return_llrs=True, used by
+ * z_sys_model/bec_model.py:19-27): logit = +llr_max (bit 1) / -llr_max (bit 0), set to 0 with
+ * probability pe per position.  polar_bec_frontend = BinarySource -> PolarEncoder -> channel in one launch;
+ * polar_bec_llr applies the channel to caller-supplied codewords (fp32 0/1, n a multiple of 4). */
+int polar_bec_frontend(uint64_t seed, uint64_t offset, float pe, float llr_max, const uint32_t *d_frozen_mask,
+                       int n, int64_t B, uint32_t *d_u_packed_out, uint32_t *d_c_packed_out, float *d_logit_out,
+                       void *stream);
+int polar_bec_llr(uint64_t seed, uint64_t offset, float pe, float llr_max, const float *d_c /*[B,n] 0/1*/,
+                  int n, int64_t B, float *d_logit_out, void *stream);
+
 /* ---- error counting ------------------------------------------------------------------------
  * count_errors / count_block_errors (my_sn/sim.py:7-18).  d_counters[0] += bit errors,
  * d_counters[1] += block errors (unsigned 64-bit, caller zeroes them). */

@@ -30,7 +30,27 @@ __device__ __forceinline__ float4 noisy_logits(const Philox &ph, uint64_t cw_id,
   return o;
 }
 
-template <int R>
+// Binary erasure channel with LLR output (my_sn/trans/channel/discrete_channel.py:79-107, return_llrs=True): logit =
+// +-llr_max for bit 1 / 0, erased to 0 with probability pe.  The reference samples the erasure pattern with a
+// Gumbel-softmax pair (:53-72), i.e. a Bernoulli(pe) draw; here one Philox word per position is compared with pe.
+__device__ __forceinline__ float4 erased_logits(const Philox &ph, uint64_t cw_id, uint32_t group, uint32_t bits4,
+                                                float pe, float llr_max) {
+  const uint4 r = ph((uint32_t)cw_id, (uint32_t)(cw_id >> 32), group, kStreamNoise);
+  const float k = 2.3283064365386963e-10f;     // 2^-32: u in [0,1)
+  float4 o;
+  o.x = ((float)r.x * k < pe) ? 0.0f : ((bits4 & 1u) ? llr_max : -llr_max);
+  o.y = ((float)r.y * k < pe) ? 0.0f : ((bits4 & 2u) ? llr_max : -llr_max);
+  o.z = ((float)r.z * k < pe) ? 0.0f : ((bits4 & 4u) ? llr_max : -llr_max);
+  o.w = ((float)r.w * k < pe) ? 0.0f : ((bits4 & 8u) ? llr_max : -llr_max);
+  return o;
+}
+template <bool BEC>
+__device__ __forceinline__ float4 channel_logits(const Philox &ph, uint64_t cw_id, uint32_t group, uint32_t bits4, float a,
+                                                 float b) {
+  return BEC ? erased_logits(ph, cw_id, group, bits4, a, b) : noisy_logits(ph, cw_id, group, bits4, a, b);
+}
+
+template <int R, bool BEC = false>
 __global__ void __launch_bounds__(256) frontend_kernel(uint64_t seed, uint64_t offset, float sigma, float scale,
                                                        const uint32_t *__restrict__ fmask, int n, int m, int64_t B,
                                                        uint32_t *__restrict__ u_out, uint32_t *__restrict__ c_out,
@@ -74,14 +94,14 @@ __global__ void __launch_bounds__(256) frontend_kernel(uint64_t seed, uint64_t o
           const uint32_t w = __shfl_sync(0xFFFFFFFFu, x[r], (it * 32 + lane) >> 3);
           if (g < ngroups) {
             const uint32_t bits4 = (w >> ((4 * g) & 31)) & 0xFu;
-            *reinterpret_cast<float4 *>(row + 4 * g) = noisy_logits(ph, id, (uint32_t)g, bits4, sigma, scale);
+            *reinterpret_cast<float4 *>(row + 4 * g) = channel_logits<BEC>(ph, id, (uint32_t)g, bits4, sigma, scale);
           }
         }
       }
     } else {  // n == 2
       const uint32_t w = __shfl_sync(0xFFFFFFFFu, x[0], 0);
       if (lane == 0) {
-        const float4 o = noisy_logits(ph, id, 0u, w & 3u, sigma, scale);
+        const float4 o = channel_logits<BEC>(ph, id, 0u, w & 3u, sigma, scale);
         row[0] = o.x; row[1] = o.y;
       }
     }
@@ -89,6 +109,7 @@ __global__ void __launch_bounds__(256) frontend_kernel(uint64_t seed, uint64_t o
 }
 
 // channel + demapper for caller-supplied codewords (fp32 0/1)
+template <bool BEC = false>
 __global__ void __launch_bounds__(256) qpsk_awgn_kernel(uint64_t seed, uint64_t offset, float sigma, float scale,
                                                         const float *__restrict__ c, int n, int64_t B,
                                                         float *__restrict__ logit) {
@@ -100,7 +121,7 @@ __global__ void __launch_bounds__(256) qpsk_awgn_kernel(uint64_t seed, uint64_t 
     const int g = (int)(i - b * ngroups);
     const float4 v = __ldg(reinterpret_cast<const float4 *>(c + b * (int64_t)n) + g);
     const uint32_t bits4 = (v.x != 0.f) | ((v.y != 0.f) << 1) | ((v.z != 0.f) << 2) | ((v.w != 0.f) << 3);
-    *reinterpret_cast<float4 *>(logit + b * (int64_t)n + 4 * g) = noisy_logits(ph, (uint64_t)b + offset, (uint32_t)g, bits4, sigma, scale);
+    *reinterpret_cast<float4 *>(logit + b * (int64_t)n + 4 * g) = channel_logits<BEC>(ph, (uint64_t)b + offset, (uint32_t)g, bits4, sigma, scale);
   }
 }
 
@@ -149,8 +170,45 @@ extern "C" int polar_qpsk_awgn_llr(uint64_t seed, uint64_t offset, float no, con
   int64_t g = (total + 255) / 256;
   const int64_t cap = (int64_t)device_sm_count() * 8;
   if (g > cap) g = cap;
-  qpsk_awgn_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(seed, offset, sigma, scale, d_c, n, B, d_logit_out);
+  qpsk_awgn_kernel<false><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(seed, offset, sigma, scale, d_c, n, B, d_logit_out);
   count_launch();
   POLAR_CHECK_LAUNCH("qpsk_awgn");
+  return POLAR_OK;
+}
+
+// ---- binary erasure channel (channel half) ------------------------------------------------------
+extern "C" int polar_bec_frontend(uint64_t seed, uint64_t offset, float pe, float llr_max, const uint32_t *d_frozen_mask,
+                                  int n, int64_t B, uint32_t *d_u_packed_out, uint32_t *d_c_packed_out, float *d_logit_out,
+                                  void *stream) {
+  if (!is_pow2(n) || n < 2 || n > POLAR_MAX_N) return set_error(POLAR_EINVAL, "bec frontend: n=%d must be a power of two in [2,%d]", n, POLAR_MAX_N);
+  if (B < 0 || !(pe >= 0.0f && pe <= 1.0f) || !(llr_max >= 0.0f)) return set_error(POLAR_EINVAL, "bec frontend: B < 0, pe outside [0,1] or llr_max < 0");
+  if (B == 0) return POLAR_OK;
+  if (!d_frozen_mask || !d_logit_out) return set_error(POLAR_EINVAL, "bec frontend: null pointer");
+  if (n >= 4 && ((uintptr_t)d_logit_out & 15)) return set_error(POLAR_EALIGN, "bec frontend: logit_out must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int m = ilog2(n);
+  const unsigned g = fe_grid(B);
+  if (n <= 1024) frontend_kernel<1, true><<<g, 256, 0, st>>>(seed, offset, pe, llr_max, d_frozen_mask, n, m, B, d_u_packed_out, d_c_packed_out, d_logit_out);
+  else if (n == 2048) frontend_kernel<2, true><<<g, 256, 0, st>>>(seed, offset, pe, llr_max, d_frozen_mask, n, m, B, d_u_packed_out, d_c_packed_out, d_logit_out);
+  else if (n == 4096) frontend_kernel<4, true><<<g, 256, 0, st>>>(seed, offset, pe, llr_max, d_frozen_mask, n, m, B, d_u_packed_out, d_c_packed_out, d_logit_out);
+  else frontend_kernel<8, true><<<g, 256, 0, st>>>(seed, offset, pe, llr_max, d_frozen_mask, n, m, B, d_u_packed_out, d_c_packed_out, d_logit_out);
+  count_launch();
+  POLAR_CHECK_LAUNCH("bec_frontend");
+  return POLAR_OK;
+}
+
+extern "C" int polar_bec_llr(uint64_t seed, uint64_t offset, float pe, float llr_max, const float *d_c, int n, int64_t B,
+                             float *d_logit_out, void *stream) {
+  if (n < 4 || (n & 3) || B < 0 || !(pe >= 0.0f && pe <= 1.0f)) return set_error(POLAR_EINVAL, "bec: n must be a multiple of 4, B >= 0, pe in [0,1]");
+  if (B == 0) return POLAR_OK;
+  if (!d_c || !d_logit_out) return set_error(POLAR_EINVAL, "bec: null pointer");
+  if (((uintptr_t)d_c & 15) || ((uintptr_t)d_logit_out & 15)) return set_error(POLAR_EALIGN, "bec: buffers must be 16-byte aligned");
+  const int64_t total = B * (int64_t)(n >> 2);
+  int64_t g = (total + 255) / 256;
+  const int64_t cap = (int64_t)device_sm_count() * 8;
+  if (g > cap) g = cap;
+  qpsk_awgn_kernel<true><<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(seed, offset, pe, llr_max, d_c, n, B, d_logit_out);
+  count_launch();
+  POLAR_CHECK_LAUNCH("bec_llr");
   return POLAR_OK;
 }

@@ -56,6 +56,8 @@ _SIGNATURES = {
   "polar_gather_cols_f32": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp]),
   "polar_rate_recover_f32": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp]),
   "polar_awgn_frontend": (_i32, [_u64, _u64, _f32, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
+  "polar_bec_frontend": (_i32, [_u64, _u64, _f32, _f32, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
+  "polar_bec_llr": (_i32, [_u64, _u64, _f32, _f32, _vp, _i32, _i64, _vp, _vp]),
   "polar_qpsk_awgn_llr": (_i32, [_u64, _u64, _f32, _vp, _i32, _i64, _vp, _vp]),
   "polar_count_errors_packed": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
   "polar_count_errors_f32": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp]),
@@ -262,6 +264,29 @@ def awgn_frontend(tables, batch_size, no, seed, offset=0, want_codeword=False):
     check(lib().polar_awgn_frontend(int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset), float(no), ptr(tables.frozen_mask), n, B,
                                     ptr(u), ptr(c), ptr(logit), stream_ptr(dev)))
   return u, c, logit
+
+
+def bec_frontend(tables, batch_size, pe, seed, offset=0, llr_max=100.0, want_codeword=False):
+  """polar_bec_frontend -> (u_packed int32 [B,words], c_packed | None, logits fp32 [B,n] in {0, +-llr_max})."""
+  dev = tables.dev
+  B, n = int(batch_size), tables.n
+  u = tc.empty((B, words(n)), dtype=tc.int32, device=dev)
+  c = tc.empty((B, words(n)), dtype=tc.int32, device=dev) if want_codeword else None
+  logit = tc.empty((B, n), dtype=tc.float32, device=dev)
+  with tc.cuda.device(dev):
+    check(lib().polar_bec_frontend(int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset), float(pe), float(llr_max),
+                                   ptr(tables.frozen_mask), n, B, ptr(u), ptr(c), ptr(logit), stream_ptr(dev)))
+  return u, c, logit
+
+
+def bec_llr(c, pe, seed, offset=0, llr_max=100.0):
+  dev = c.device
+  c2 = c.to(tc.float32).reshape(-1, c.shape[-1]).contiguous()
+  out = tc.empty_like(c2)
+  with tc.cuda.device(dev):
+    check(lib().polar_bec_llr(int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset), float(pe), float(llr_max), ptr(c2), c2.shape[1],
+                              c2.shape[0], ptr(out), stream_ptr(dev)))
+  return out.reshape(c.shape)
 
 
 def qpsk_awgn_llr(c, no, seed, offset=0):

@@ -426,3 +426,54 @@ def test_5g_encoder_decoder_wrappers():
         assert torch.equal(Polar5GDecoder(enc, dec_type="SCL")(clean), u)
     with pytest.raises(Exception):
         Polar5GEncoder(30, 108, channel_type="downlink")(torch.zeros(2, 30).cuda())
+
+
+def test_bec_channel_and_link_model():
+    """SURVEY 8f N4 (channel half): polar_bec_frontend / polar_bec_llr statistics, the BinaryErasureChannel layer in both
+    output modes, and System_BEC_model's BLER inside the confidence band of the oracle SC decoder on independent erasures."""
+    torch, dk, po, co, dev = _env()
+    from types import SimpleNamespace
+    from polar.enc import PolarEncoder
+    from polar.polar_sc import SC_Dec
+    from z_sys_model.bec_model import System_BEC_model
+    from my_sn.trans.channel.discrete_channel import BinaryErasureChannel
+    n, k, B, pe = 256, 128, 40000, 0.35
+    fp = po.rm_frozen_pos(n, n - k)
+    tables = dk.code_tables(fp, n, dev)
+    u, c, llr = dk.bec_frontend(tables, B, pe, seed=7, want_codeword=True)
+    x = llr.cpu().numpy()
+    cb = unpack_words(c.cpu().numpy(), n)
+    er = x == 0
+    assert abs(er.mean() - pe) < 5 * np.sqrt(pe * (1 - pe) / x.size)
+    assert np.array_equal(x[~er], np.where(cb[~er] == 1, 100.0, -100.0).astype(np.float32))
+    assert abs(er[:, 0].mean() - pe) < 6 * np.sqrt(pe * (1 - pe) / B) and abs(er[:, n - 1].mean() - pe) < 6 * np.sqrt(pe * (1 - pe) / B)
+    u2, _, llr2 = dk.bec_frontend(tables, B, pe, seed=7)
+    assert torch.equal(llr, llr2) and torch.equal(u, u2)                      # pure function of (seed, offset)
+    # layer API
+    ch = BinaryErasureChannel(return_llrs=True)
+    bits = torch.randint(0, 2, (500, n), device=dev, dtype=torch.float32)
+    y = ch([bits, 0.2])
+    assert set(np.unique(y.cpu().numpy())) <= {-100.0, 0.0, 100.0} and abs((y == 0).float().mean().item() - 0.2) < 0.01
+    assert torch.equal(y[y != 0], torch.where(bits[y != 0] == 1, 100.0, -100.0))
+    t = BinaryErasureChannel(return_llrs=False)([bits, 0.5])
+    assert set(np.unique(t.cpu().numpy())) <= {-1.0, 0.0, 1.0} and torch.equal(t[t >= 0], bits[t >= 0])
+    tb = BinaryErasureChannel(return_llrs=False, bipolar_input=True)([2 * bits - 1, 0.5])
+    assert set(np.unique(tb.cpu().numpy())) <= {-1.0, 0.0, 1.0} and torch.equal(tb[tb != 0], (2 * bits - 1)[tb != 0])
+    with pytest.raises(AssertionError):
+        BinaryErasureChannel(return_llrs=True)([bits + 2, 0.1])
+    # link model vs oracle
+    cfg = SimpleNamespace(n=n, k=k)
+    model = System_BEC_model(cfg, PolarEncoder(fp, n, None), SC_Dec(fp, n), seed=5)
+    b, bh = model(B, pe)
+    bler = (b != bh).any(-1).float().mean().item()
+    rng = np.random.default_rng(3)
+    ub = rng.integers(0, 2, (8000, k)).astype(np.uint8)
+    cw = po.encode(ub, fp, n)
+    lg = np.where(cw == 1, 100.0, -100.0).astype(np.float32)
+    lg[rng.random(lg.shape) < pe] = 0.0
+    ref = co.sc_decode_full(lg, po.frozen_vec(fp, n))[:, po.info_positions(fp, n)]
+    p_ref = np.any(ref != ub, axis=1).mean()
+    assert abs(bler - p_ref) < 6 * np.sqrt(max(p_ref, 1e-3) * (1 - p_ref) / 8000)
+    m2 = System_BEC_model(cfg, PolarEncoder(fp, n, None), SC_Dec(fp, n), fused=False)
+    b2, bh2 = m2(8000, pe)
+    assert abs((b2 != bh2).any(-1).float().mean().item() - p_ref) < 8 * np.sqrt(max(p_ref, 1e-3) * (1 - p_ref) / 8000)
