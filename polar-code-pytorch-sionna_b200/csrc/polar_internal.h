@@ -24,6 +24,13 @@ int launch_sc3(const float *logit, const uint32_t *fmask, int n, int64_t B, uint
 int launch_sc4(const float *logit, const uint32_t *fmask, int n, int64_t B, uint32_t *u_packed, float *u_info,
                const int32_t *info_pos, int k, int warps, cudaStream_t st);
 
+// polar_scl3.cu: SCL decoder with compile-time tree, virtual top stages and on-chip LLR tree (n in [256, 4096], L in [2, 32])
+struct Scl3Plan { int64_t grid; size_t ws_bytes_per_warp; };
+bool scl3_supported(int n, int L);
+int launch_scl3(const float *logit, const uint32_t *fmask, int n, int L, int64_t B, uint32_t *best, float *u_info,
+                const int32_t *info_pos, int k, double *pm_out, uint32_t *list, const uint32_t *crc_rows, int crc_len,
+                void *ws, cudaStream_t st, Scl3Plan *plan_only);
+
 inline bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
 
 #define POLAR_CHECK_LAUNCH(what)                                                           \

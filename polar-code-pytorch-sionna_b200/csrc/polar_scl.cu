@@ -580,13 +580,13 @@ __global__ void __launch_bounds__(128, SCL2_MINB) scl2_kernel(const SclParams P)
 
 struct SclPlan { int s_glob; size_t smem_per_warp; size_t ws_doubles_per_warp; int warps_per_cta; int64_t grid; int words_global = 0; };
 
-static int scl_mode() { return env_int("POLAR_SCL_MODE", 1); }   // 1: lane = (codeword, path) [default]; 0: warp per codeword
+static int scl_mode() { return env_int("POLAR_SCL_MODE", 2); }   // 2: scl3 where supported, else 1 [default]; 1: lane = (codeword, path); 0: warp per codeword
 
 static SclPlan scl_plan(int n, int L, int64_t B) {
   SclPlan pl;
   const int m = ilog2(n);
   const int max_smem = device_max_smem_optin();
-  if (scl_mode() == 1) {
+  if (scl_mode() >= 1) {
     const int nw = n < 32 ? 1 : n >> 5;
     const size_t words = (size_t)32 * 2 * nw * 4;
     const int budget = env_int("POLAR_SCL_SMEM_KB", 4) * 1024;    // per warp
@@ -641,7 +641,7 @@ static SclPlan scl_plan(int n, int L, int64_t B) {
 
 template <int L>
 static int launch_scl(SclParams &P, const SclPlan &pl, cudaStream_t st) {
-  void (*kern)(const SclParams) = (scl_mode() == 1) ? scl2_kernel<L> : scl_kernel<L>;
+  void (*kern)(const SclParams) = (scl_mode() >= 1) ? scl2_kernel<L> : scl_kernel<L>;
   const size_t smem = pl.smem_per_warp * pl.warps_per_cta;
   if (smem > (size_t)device_max_smem_optin()) return set_error(POLAR_ENOMEM, "scl: needs %zu B shared memory per CTA", smem);
   POLAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -658,7 +658,17 @@ using namespace polar;
 extern "C" size_t polar_scl_workspace_bytes(int n, int L, int64_t B) {
   if (!is_pow2(n) || n < 2 || n > POLAR_SCL_MAX_N || !is_pow2(L) || L > POLAR_SCL_MAX_L || B <= 0) return 0;
   const SclPlan pl = scl_plan(n, L, B);
-  return (size_t)pl.grid * pl.warps_per_cta * pl.ws_doubles_per_warp * sizeof(double);
+  size_t need = (size_t)pl.grid * pl.warps_per_cta * pl.ws_doubles_per_warp * sizeof(double);
+#if !defined(POLAR_F_BOXPLUS)
+  if (scl_mode() == 2 && scl3_supported(n, L)) {   // the larger of the two mappings: misaligned rows fall back to scl2
+    Scl3Plan p3;
+    if (launch_scl3(nullptr, nullptr, n, L, B, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, &p3) == POLAR_OK) {
+      const size_t n3 = (size_t)p3.grid * p3.ws_bytes_per_warp;
+      if (n3 > need) need = n3;
+    }
+  }
+#endif
+  return need;
 }
 
 extern "C" int polar_scl_decode(const float *d_logit, const uint32_t *d_frozen_mask, int n, int L, int64_t B,
@@ -673,6 +683,19 @@ extern "C" int polar_scl_decode(const float *d_logit, const uint32_t *d_frozen_m
   if (!d_best_packed && !d_u_info_f32 && !d_pm_sorted && !d_list_packed) return set_error(POLAR_EINVAL, "scl: no output buffer");
   if (d_u_info_f32 && (!d_info_pos || k < 0 || k > n)) return set_error(POLAR_EINVAL, "scl: u_info requested without valid info_pos/k");
   if (crc_len < 0 || crc_len > 32 || (crc_len > 0 && !d_crc_rows)) return set_error(POLAR_EINVAL, "scl: bad crc_len / crc_rows");
+#if !defined(POLAR_F_BOXPLUS)
+  if (scl_mode() == 2 && scl3_supported(n, L) && ((uintptr_t)d_logit & 15) == 0) {
+    Scl3Plan p3;
+    int rc = launch_scl3(d_logit, d_frozen_mask, n, L, B, d_best_packed, d_u_info_f32, d_info_pos, k, d_pm_sorted, d_list_packed,
+                         d_crc_rows, crc_len, d_workspace, (cudaStream_t)stream, &p3);
+    if (rc != POLAR_OK) return rc;
+    const size_t need3 = (size_t)p3.grid * p3.ws_bytes_per_warp;
+    if (!d_workspace || workspace_bytes < need3) return set_error(POLAR_ENOMEM, "scl: workspace %zu B < required %zu B", workspace_bytes, need3);
+    if ((uintptr_t)d_workspace & 255) return set_error(POLAR_EALIGN, "scl: workspace must be 256-byte aligned");
+    return launch_scl3(d_logit, d_frozen_mask, n, L, B, d_best_packed, d_u_info_f32, d_info_pos, k, d_pm_sorted, d_list_packed,
+                       d_crc_rows, crc_len, d_workspace, (cudaStream_t)stream, nullptr);
+  }
+#endif
   const SclPlan pl = scl_plan(n, L, B);
   const size_t need = (size_t)pl.grid * pl.warps_per_cta * pl.ws_doubles_per_warp * sizeof(double);
   if (need > 0) {

@@ -115,6 +115,40 @@ def main():
                           (L, n, B, kb, warps, best, B / best * 1e3, B / best * 1e3 * k / 1e9), flush=True)
                 except Exception as e:
                     print("SCL kb=%d warps=%d failed: %s" % (kb, warps, e))
+    elif what == "sptest":
+        import ctypes
+        cnt = torch.zeros(3, dtype=torch.int64, device=dev)
+        N = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 28
+        dk.lib().polar_scl3_math_selftest.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
+        dk.check(dk.lib().polar_scl3_math_selftest(N, dk.ptr(cnt), dk.stream_ptr(dev)))
+        torch.cuda.synchronize()
+        print("softplus selftest: %d arguments, mismatches exp/log/softplus vs CUDA math library:" % N, cnt.tolist(), flush=True)
+    elif what == "scl3":
+        # scl3 tuning sweep + differential check against scl2 on the same inputs (decisions, all PMs, lists)
+        L = int(os.environ.get("L", "8"))
+        B = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 15
+        ebno = float(os.environ.get("EBNO", "3.0"))
+        _, _, x = dk.awgn_frontend(tables, B, po.ebnodb2no(ebno, 2, k / n), 1234)
+        os.environ["POLAR_SCL_MODE"] = "1"
+        ref = dk.scl_decode(x, tables, L, want_packed=True, want_info=False, want_pm=True, want_list=True)
+        torch.cuda.synchronize()
+        best, med = timeit(lambda: dk.scl_decode(x, tables, L, want_packed=True, want_info=False), iters=3, warm=1)
+        print("scl2 L=%d n=%d B=%d: %8.3f ms  %.3e cw/s  %.3f Gbit/s info" % (L, n, B, best, B / best * 1e3, B / best * 1e3 * k / 1e9), flush=True)
+        os.environ["POLAR_SCL_MODE"] = "2"
+        for ss in [int(v) for v in os.environ.get("SS", "5,6,7").split(",")]:
+            for ctas in [int(v) for v in os.environ.get("CTAS", "0").split(",")]:
+                os.environ["POLAR_SCL3_SS"] = str(ss); os.environ["POLAR_SCL3_CTAS"] = str(ctas)
+                try:
+                    got = dk.scl_decode(x, tables, L, want_packed=True, want_info=False, want_pm=True, want_list=True)
+                    torch.cuda.synchronize()
+                    d_best = int((got["u_packed"] != ref["u_packed"]).any(dim=1).sum())
+                    d_list = int((got["list"] != ref["list"]).any(dim=2).any(dim=1).sum())
+                    rel = ((got["pm"] - ref["pm"]).abs() / ref["pm"].abs().clamp_min(1e-30)).max().item()
+                    best, med = timeit(lambda: dk.scl_decode(x, tables, L, want_packed=True, want_info=False), iters=3, warm=1)
+                    print("scl3 L=%d n=%d B=%d SS=%d ctas=%d: %8.3f ms  %.3e cw/s  %.3f Gbit/s info | vs scl2: best-path diffs %d, list diffs %d, max rel pm %.2e" %
+                          (L, n, B, ss, ctas, best, B / best * 1e3, B / best * 1e3 * k / 1e9, d_best, d_list, rel), flush=True)
+                except Exception as e:
+                    print("scl3 SS=%d ctas=%d failed: %s" % (ss, ctas, e), flush=True)
     elif what == "fe":
         B = int(sys.argv[3]) if len(sys.argv) > 3 else (1 << 28) // n
         f = lambda: dk.awgn_frontend(tables, B, no, 1234)
