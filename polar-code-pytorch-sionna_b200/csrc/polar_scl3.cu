@@ -16,7 +16,9 @@
 //   * Leaf: log(1+exp(.)) stays literal (ties between path metrics are decided by their last bit, see
 //     polar_softplus.cuh) but runs the math library's exp / log operation sequences without their out-of-domain
 //     branches and with the coefficients in constant memory: ~65 instead of 163 instructions per penalty.
-// Launched with ONE warp per CTA (no inter-warp synchronisation anywhere).
+// CTAs of 4 independent warps (16 warps per SM); the warps of a CTA meet at a barrier every few leaves so that they run
+// the same code at the same time: the kernel is ~70 KB of mostly straight-line code, and 16-32 unsynchronised
+// warps missed the SM instruction cache 10-22 % of the time (ncu: GPC instruction-fetch path 76-86 % busy).
 #include <math.h>
 #include <type_traits>
 
@@ -35,7 +37,7 @@ struct Params {
   const float *logit; const uint32_t *fmask; int64_t B;
   uint32_t *best; float *u_info; const int32_t *info_pos; int k;
   double *pm_out; uint32_t *list; const uint32_t *crc_rows; int crc_len;
-  unsigned char *ws; size_t ws_bytes_per_warp;
+  unsigned char *ws; size_t ws_bytes_per_warp; int sync_mask;
 };
 
 // ---- f / g on fp32 (exact for f) and fp64 ----------------------------------------------------------
@@ -79,15 +81,17 @@ struct Cfg {
   static constexpr size_t ws_bytes = ((gl_doubles * 8 + word_count * 4 + 255) / 256) * 256;
 };
 
-template <int M, int L, int SS_, int MINB>
-__global__ void __launch_bounds__(32, MINB) scl3_kernel(const Params P) {
+// WPC warps per CTA, CPS CTAs per SM (register budget).  The warps of a CTA are independent decoders; they only meet at
+// a barrier every `sync_mask + 1` leaves, which keeps them on the same few KB of code (see the header comment).
+template <int M, int L, int SS_, int WPC, int CPS>
+__global__ void __launch_bounds__(32 * WPC, CPS) scl3_kernel(const Params P) {
   using C = Cfg<M, L, SS_>;
   constexpr int N = C::N, NW = C::NW, TOP = C::TOP, SS = C::SS, HT = C::HT, CPW = C::CPW, LOGL = C::LOGL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *const llr_s = reinterpret_cast<double *>(smem_raw);
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *const llr_s = reinterpret_cast<double *>(smem_raw + (size_t)warp * C::smem_bytes);
   const int p = lane & (L - 1), gbase = lane & ~(L - 1), cwl = lane >> LOGL;
-  unsigned char *const wsb = P.ws + (size_t)blockIdx.x * P.ws_bytes_per_warp;
+  unsigned char *const wsb = P.ws + ((size_t)blockIdx.x * WPC + warp) * P.ws_bytes_per_warp;
   double *const llr_g = reinterpret_cast<double *>(wsb);
   uint32_t *const bl = reinterpret_cast<uint32_t *>(wsb + C::gl_doubles * 8);   // stage s>=5 at (2^(s-5)-1)*32
   uint32_t *const rootw = bl + (size_t)32 * NW;                                  // [NW][32]
@@ -206,18 +210,14 @@ __global__ void __launch_bounds__(32, MINB) scl3_kernel(const Params P) {
       }
     }
   };
-  // f cascade: stages S-1 .. 0 from stage S
-  auto fcasc = [&](auto sc, auto &&self) -> void {
-    constexpr int S = decltype(sc)::value;
-    if constexpr (S >= 1) {
-      fstep(sc);
-      self(std::integral_constant<int, S - 1>{}, self);
-    }
-  };
-
-  for (int64_t bb = blockIdx.x; bb < nbatch; bb += gridDim.x) {
+  // every warp of the CTA runs the same number of batches (the barriers below need all of them); a batch past the end
+  // decodes the last codeword again and stores nothing
+  const int64_t bstride = (int64_t)gridDim.x * WPC;
+  const int64_t rounds = (nbatch + bstride - 1) / bstride;
+  for (int64_t rd = 0; rd < rounds; ++rd) {
+    const int64_t bb = rd * bstride + (int64_t)blockIdx.x * WPC + warp;
     const int64_t b = bb * CPW + cwl;
-    const bool valid = b < P.B;
+    const bool valid = bb < nbatch && b < P.B;
     ch = P.logit + (valid ? b : (P.B - 1)) * (int64_t)N;
     double pm = (p == 0) ? 0.0 : kLlrMaxD;                       // polar_scl.py:192-194
     rowL = idrow; rowB = idrow; small = 0u;
@@ -225,9 +225,16 @@ __global__ void __launch_bounds__(32, MINB) scl3_kernel(const Params P) {
 
 #pragma unroll 1
     for (int i = 0; i < N; ++i) {
+      if constexpr (WPC > 1) {
+        if ((i & P.sync_mask) == 0) __syncthreads();
+      }
       if ((i & 31) == 0) fword = __ldg(P.fmask + (i >> 5));
       // ------------------------------------------------------------------ descent to leaf i
       const int t = (i == 0) ? M : (__ffs(i) - 1);
+      // every f / g step exists exactly once in the binary: a g (or virtual-pass) switch, then ONE fall-through f
+      // cascade.  (Inlining the cascade into each case replicated the low f steps seven times; the kernel then
+      // missed the SM instruction cache 10-22 % of the time and ran at the GPC instruction-fetch limit --
+      // ncu: gcc__cache_requests_type_instruction at 76-86 % of peak.)
       if (t >= TOP) {
         switch (i >> TOP) {
           case 0: vpass(std::integral_constant<int, 0>{}); break;
@@ -239,22 +246,22 @@ __global__ void __launch_bounds__(32, MINB) scl3_kernel(const Params P) {
           case 6: vpass(std::integral_constant<int, 6>{}); break;
           default: vpass(std::integral_constant<int, 7>{}); break;
         }
-        fcasc(std::integral_constant<int, TOP>{}, fcasc);
       } else {
-#define POLAR_SCL3_CASE(T)                                                                 \
-  case T:                                                                                  \
-    if constexpr (T < TOP) {                                                               \
-      gstep(std::integral_constant<int, T>{});                                             \
-      fcasc(std::integral_constant<int, T>{}, fcasc);                                      \
-    }                                                                                      \
-    break;
+#define POLAR_SCL3_G(T) case T: if constexpr (T < TOP) gstep(std::integral_constant<int, T>{}); break;
         switch (t) {
-          POLAR_SCL3_CASE(0) POLAR_SCL3_CASE(1) POLAR_SCL3_CASE(2) POLAR_SCL3_CASE(3) POLAR_SCL3_CASE(4)
-          POLAR_SCL3_CASE(5) POLAR_SCL3_CASE(6) POLAR_SCL3_CASE(7) POLAR_SCL3_CASE(8)
+          POLAR_SCL3_G(0) POLAR_SCL3_G(1) POLAR_SCL3_G(2) POLAR_SCL3_G(3) POLAR_SCL3_G(4)
+          POLAR_SCL3_G(5) POLAR_SCL3_G(6) POLAR_SCL3_G(7) POLAR_SCL3_G(8)
           default: break;
         }
-#undef POLAR_SCL3_CASE
+#undef POLAR_SCL3_G
       }
+#define POLAR_SCL3_F(S) case S: if constexpr (S <= TOP) fstep(std::integral_constant<int, S>{}); [[fallthrough]];
+      switch (t < TOP ? t : TOP) {
+        POLAR_SCL3_F(9) POLAR_SCL3_F(8) POLAR_SCL3_F(7) POLAR_SCL3_F(6) POLAR_SCL3_F(5)
+        POLAR_SCL3_F(4) POLAR_SCL3_F(3) POLAR_SCL3_F(2) POLAR_SCL3_F(1)
+        default: break;
+      }
+#undef POLAR_SCL3_F
       {  // stages 0..min(t, TOP) were rewritten by this path into its own slot
         const int top = (t < TOP ? t : TOP);
         const unsigned long long msk = (1ull << (5 * (top + 1))) - 1ull;
@@ -394,27 +401,29 @@ __global__ void __launch_bounds__(32, MINB) scl3_kernel(const Params P) {
   }
 }
 
-template <int M, int L, int SS_, int MINB>
-static int launch_one(const Params &P0, int64_t grid_cap_per_sm, cudaStream_t st, Scl3Plan *plan_only, int64_t B) {
+template <int M, int L, int SS_, int WPC, int CPS>
+static int launch_one(const Params &P0, int64_t cta_cap_per_sm, cudaStream_t st, Scl3Plan *plan_only, int64_t B) {
   using C = Cfg<M, L, SS_>;
-  int ctas_per_sm = (int)((size_t)(227 * 1024) / (C::smem_bytes + 1024));
-  if (ctas_per_sm > MINB) ctas_per_sm = MINB;
-  if (grid_cap_per_sm > 0 && ctas_per_sm > grid_cap_per_sm) ctas_per_sm = (int)grid_cap_per_sm;
+  constexpr size_t smem_cta = C::smem_bytes * WPC;
+  int ctas_per_sm = (int)((size_t)(227 * 1024) / (smem_cta + 1024));
+  if (ctas_per_sm > CPS) ctas_per_sm = CPS;
+  if (cta_cap_per_sm > 0 && ctas_per_sm > cta_cap_per_sm) ctas_per_sm = (int)cta_cap_per_sm;
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   const int64_t nbatch = (B + C::CPW - 1) / C::CPW;
   int64_t grid = (int64_t)device_sm_count() * ctas_per_sm;
-  if (grid > nbatch) grid = nbatch;
+  if (grid > (nbatch + WPC - 1) / WPC) grid = (nbatch + WPC - 1) / WPC;
   if (grid < 1) grid = 1;
   if (plan_only) {
-    plan_only->grid = grid;
+    plan_only->grid = grid * WPC;                 // in warps
     plan_only->ws_bytes_per_warp = C::ws_bytes;
     return POLAR_OK;
   }
   Params P = P0;
   P.ws_bytes_per_warp = C::ws_bytes;
-  auto kern = scl3_kernel<M, L, SS_, MINB>;
-  POLAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes));
-  kern<<<(unsigned)grid, 32, C::smem_bytes, st>>>(P);
+  auto kern = scl3_kernel<M, L, SS_, WPC, CPS>;
+  if (smem_cta > (size_t)device_max_smem_optin()) return set_error(POLAR_ENOMEM, "scl3: needs %zu B shared memory per CTA", smem_cta);
+  POLAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cta));
+  kern<<<(unsigned)grid, 32 * WPC, smem_cta, st>>>(P);
   count_launch();
   POLAR_CHECK_LAUNCH("scl3_kernel");
   return POLAR_OK;
@@ -461,14 +470,29 @@ int launch_scl3(const float *logit, const uint32_t *fmask, int n, int L, int64_t
   P.pm_out = pm_out; P.list = list; P.crc_rows = crc_rows; P.crc_len = crc_len;
   P.ws = (unsigned char *)ws; P.ws_bytes_per_warp = 0;
   const int m = ilog2(n);
-  const int ss = env_int("POLAR_SCL3_SS", 6);
+  const int ss = env_int("POLAR_SCL3_SS", 54);
+  P.sync_mask = env_int("POLAR_SCL3_SYNC", 4) - 1;
   const int64_t cap = env_int("POLAR_SCL3_CTAS", 0);
+#if defined(POLAR_SCL3_DEV)
 #define POLAR_SCL3_L(MM, LL)                                                                          \
   if (L == LL) {                                                                                       \
-    if (ss <= 5) return scl3::launch_one<MM, LL, 5, 16>(P, cap, st, plan_only, B);                     \
-    if (ss == 6) return scl3::launch_one<MM, LL, 6, 13>(P, cap, st, plan_only, B);                     \
-    return scl3::launch_one<MM, LL, 7, 6>(P, cap, st, plan_only, B);                                   \
+    if (ss == 51) return scl3::launch_one<MM, LL, 5, 1, 16>(P, cap, st, plan_only, B);                 \
+    if (ss == 54) return scl3::launch_one<MM, LL, 5, 4, 4>(P, cap, st, plan_only, B);                  \
+    if (ss == 58) return scl3::launch_one<MM, LL, 5, 8, 2>(P, cap, st, plan_only, B);                  \
+    if (ss == 516) return scl3::launch_one<MM, LL, 5, 16, 1>(P, cap, st, plan_only, B);                \
+    if (ss == 583) return scl3::launch_one<MM, LL, 5, 8, 3>(P, cap, st, plan_only, B);                 \
+    if (ss == 5122) return scl3::launch_one<MM, LL, 5, 12, 2>(P, cap, st, plan_only, B);               \
+    if (ss == 574) return scl3::launch_one<MM, LL, 5, 7, 4>(P, cap, st, plan_only, B);                 \
+    if (ss == 48) return scl3::launch_one<MM, LL, 4, 8, 4>(P, cap, st, plan_only, B);                  \
+    if (ss == 416) return scl3::launch_one<MM, LL, 4, 16, 2>(P, cap, st, plan_only, B);                \
+    if (ss == 412) return scl3::launch_one<MM, LL, 4, 12, 2>(P, cap, st, plan_only, B);                \
+    if (ss == 68) return scl3::launch_one<MM, LL, 6, 6, 2>(P, cap, st, plan_only, B);                  \
+    return scl3::launch_one<MM, LL, 5, 4, 4>(P, cap, st, plan_only, B);                                \
   }
+#else
+#define POLAR_SCL3_L(MM, LL)                                                                          \
+  if (L == LL) return scl3::launch_one<MM, LL, 5, 4, 4>(P, cap, st, plan_only, B);
+#endif
 #if defined(POLAR_SCL3_DEV)
 #define POLAR_SCL3_M(MM) if (m == MM) { POLAR_SCL3_L(MM, 8) }
   POLAR_SCL3_M(10)
