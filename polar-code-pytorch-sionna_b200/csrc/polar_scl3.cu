@@ -223,63 +223,71 @@ __global__ void __launch_bounds__(32 * WPC, CPS) scl3_kernel(const Params P) {
     rowL = idrow; rowB = idrow; small = 0u;
     uint32_t fword = 0u;
 
+    // One iteration = one PAIR of leaves (i0, i0+1) under a stage-1 node.  The stage-0 LLRs never leave registers, the
+    // odd leaf needs no dispatch at all, and a frozen-frozen pair (no fork possible) evaluates its two penalties as
+    // independent instruction streams.
 #pragma unroll 1
-    for (int i = 0; i < N; ++i) {
+    for (int pr = 0; pr < N / 2; ++pr) {
+      const int i0 = 2 * pr;
       if constexpr (WPC > 1) {
-        if ((i & P.sync_mask) == 0) __syncthreads();
+        if ((pr & P.sync_mask) == 0) __syncthreads();
       }
-      if ((i & 31) == 0) fword = __ldg(P.fmask + (i >> 5));
-      // ------------------------------------------------------------------ descent to leaf i
-      const int t = (i == 0) ? M : (__ffs(i) - 1);
-      // every f / g step exists exactly once in the binary: a g (or virtual-pass) switch, then ONE fall-through f
-      // cascade.  (Inlining the cascade into each case replicated the low f steps seven times; the kernel then
-      // missed the SM instruction cache 10-22 % of the time and ran at the GPC instruction-fetch limit --
-      // ncu: gcc__cache_requests_type_instruction at 76-86 % of peak.)
-      if (t >= TOP) {
-        switch (i >> TOP) {
-          case 0: vpass(std::integral_constant<int, 0>{}); break;
-          case 1: vpass(std::integral_constant<int, 1>{}); break;
-          case 2: vpass(std::integral_constant<int, 2>{}); break;
-          case 3: vpass(std::integral_constant<int, 3>{}); break;
-          case 4: vpass(std::integral_constant<int, 4>{}); break;
-          case 5: vpass(std::integral_constant<int, 5>{}); break;
-          case 6: vpass(std::integral_constant<int, 6>{}); break;
-          default: vpass(std::integral_constant<int, 7>{}); break;
-        }
+      __syncwarp();
+      if ((i0 & 31) == 0) fword = __ldg(P.fmask + (i0 >> 5));
+      const unsigned fz = (fword >> (i0 & 31)) & 3u;             // bit 0 / 1: leaf i0 / i0+1 frozen
+      // ------------------------------------------------------------------ descent to the stage-1 node
+      const int t = (i0 == 0) ? M : (__ffs(i0) - 1);             // >= 1
+      double l1a, l1b;
+      if (t == 1) {
+        // g: stage 2 (slot of the ancestor that wrote it) -> stage 1, beta = the left pair's partial sums
+        const double *src = llr_s + 32 * 3 + gbase + (unsigned)((rowL >> 10) & 31u);
+        const uint32_t ub = small >> 1;
+        l1a = gop(src[0], src[2 * 32], ub & 1u);
+        l1b = gop(src[1 * 32], src[3 * 32], (ub >> 1) & 1u);
       } else {
+        // every f / g step exists exactly once in the binary: a g (or virtual-pass) switch, then ONE fall-through f
+        // cascade down to stage 2.
+        if (t >= TOP) {
+          switch (i0 >> TOP) {
+            case 0: vpass(std::integral_constant<int, 0>{}); break;
+            case 1: vpass(std::integral_constant<int, 1>{}); break;
+            case 2: vpass(std::integral_constant<int, 2>{}); break;
+            case 3: vpass(std::integral_constant<int, 3>{}); break;
+            case 4: vpass(std::integral_constant<int, 4>{}); break;
+            case 5: vpass(std::integral_constant<int, 5>{}); break;
+            case 6: vpass(std::integral_constant<int, 6>{}); break;
+            default: vpass(std::integral_constant<int, 7>{}); break;
+          }
+        } else {
 #define POLAR_SCL3_G(T) case T: if constexpr (T < TOP) gstep(std::integral_constant<int, T>{}); break;
-        switch (t) {
-          POLAR_SCL3_G(0) POLAR_SCL3_G(1) POLAR_SCL3_G(2) POLAR_SCL3_G(3) POLAR_SCL3_G(4)
-          POLAR_SCL3_G(5) POLAR_SCL3_G(6) POLAR_SCL3_G(7) POLAR_SCL3_G(8)
+          switch (t) {
+            POLAR_SCL3_G(2) POLAR_SCL3_G(3) POLAR_SCL3_G(4)
+            POLAR_SCL3_G(5) POLAR_SCL3_G(6) POLAR_SCL3_G(7) POLAR_SCL3_G(8)
+            default: break;
+          }
+#undef POLAR_SCL3_G
+        }
+#define POLAR_SCL3_F(S) case S: if constexpr (S <= TOP) fstep(std::integral_constant<int, S>{}); [[fallthrough]];
+        switch (t < TOP ? t : TOP) {
+          POLAR_SCL3_F(9) POLAR_SCL3_F(8) POLAR_SCL3_F(7) POLAR_SCL3_F(6) POLAR_SCL3_F(5)
+          POLAR_SCL3_F(4) POLAR_SCL3_F(3)
           default: break;
         }
-#undef POLAR_SCL3_G
-      }
-#define POLAR_SCL3_F(S) case S: if constexpr (S <= TOP) fstep(std::integral_constant<int, S>{}); [[fallthrough]];
-      switch (t < TOP ? t : TOP) {
-        POLAR_SCL3_F(9) POLAR_SCL3_F(8) POLAR_SCL3_F(7) POLAR_SCL3_F(6) POLAR_SCL3_F(5)
-        POLAR_SCL3_F(4) POLAR_SCL3_F(3) POLAR_SCL3_F(2) POLAR_SCL3_F(1)
-        default: break;
-      }
 #undef POLAR_SCL3_F
-      {  // stages 0..min(t, TOP) were rewritten by this path into its own slot
+        const double *src = llr_s + 32 * 3 + lane;               // stage 2, own slot
+        l1a = fop(src[0], src[2 * 32]);
+        l1b = fop(src[1 * 32], src[3 * 32]);
+      }
+      {  // stages 1..min(t, TOP) now belong to this path (own slot); stage 0 lives in registers only
         const int top = (t < TOP ? t : TOP);
-        const unsigned long long msk = (1ull << (5 * (top + 1))) - 1ull;
+        const unsigned long long msk = ((1ull << (5 * (top + 1))) - 1ull) & ~31ull;
         rowL = (rowL & ~msk) | (idrow & msk);
       }
-      // ------------------------------------------------------------------ leaf
-      const double x = llr_s[lane];
-      const double xc = fmax(fmin(x, kLlrMaxD), -kLlrMaxD);       // polar_scl.py:81
-      // polar_scl.py:82-83: pm += log(1 + exp(-(1-2u).xc)), evaluated literally (polar_softplus.cuh)
-      const double pen0 = sp::softplus_literal(-xc);             // u = 0
-      unsigned bit = 0u;
-      if ((fword >> (i & 31)) & 1u) {
-        pm += pen0;                                              // frozen: u = 0
-      } else {
-        // fork: candidate E = u*L + p  (reference slot order [u=0 paths | u=1 paths], polar_scl.py:49-68);
-        // two candidates per lane, bitonic sort of the 2L candidates of each codeword inside its lane group
-        const double pen1 = sp::softplus_literal(xc);            // u = 1
-        double k0 = pm + pen0, k1 = pm + pen1;
+      // info leaf: fork every path, rank the 2L candidates, keep L.  Candidate E = u*L + p (reference slot order
+      // [u=0 paths | u=1 paths], polar_scl.py:49-68); two candidates per lane, bitonic sort inside the lane group.
+      auto info_leaf = [&](double x) -> unsigned {
+        const double xc = fmax(fmin(x, kLlrMaxD), -kLlrMaxD);     // polar_scl.py:81
+        double k0 = pm + sp::softplus_literal(-xc), k1 = pm + sp::softplus_literal(xc);   // u = 0 / u = 1
         int s0 = p, s1 = L + p;
 #pragma unroll
         for (int k = 2; k <= 2 * L; k <<= 1) {
@@ -302,20 +310,49 @@ __global__ void __launch_bounds__(32 * WPC, CPS) scl3_kernel(const Params P) {
           }
         }
         const int parent = gbase + (s0 & (L - 1));
-        bit = (unsigned)(s0 >> LOGL) & 1u;
         pm = k0;
         rowL = __shfl_sync(FULL, rowL, parent);
         rowB = __shfl_sync(FULL, rowB, parent);
         small = __shfl_sync(FULL, small, parent);
+        __syncwarp();   // forked paths read their parents' slots from here on
+        return (unsigned)(s0 >> LOGL) & 1u;
+      };
+      auto frozen_pen = [&](double x) -> double {                // polar_scl.py:82-83 with u = 0
+        return sp::softplus_literal(-fmax(fmin(x, kLlrMaxD), -kLlrMaxD));
+      };
+      // ------------------------------------------------------------------ the two leaves
+      const double x0 = fop(l1a, l1b);
+      uint32_t cur;                                                // partial sums of the pair: (u0 ^ u1, u1)
+      if (fz == 3u) {
+        const double pen0 = frozen_pen(x0), pen1 = frozen_pen(__dadd_rn(l1a, l1b));   // g with u0 = 0
+        pm += pen0;
+        pm += pen1;
+        cur = 0u;
+      } else {
+        double x1;
+        if (fz & 1u) {
+          pm += frozen_pen(x0);
+          x1 = __dadd_rn(l1a, l1b);
+          small &= ~1u;
+        } else {
+          double *st1 = llr_s + 32 * 1 + lane;                    // stage 1, own slot: the children read it after the fork
+          st1[0] = l1a; st1[32] = l1b;
+          const unsigned u0 = info_leaf(x0);
+          small = (small & ~1u) | u0;                              // travels with the path through the next fork
+          const double *q1 = llr_s + 32 * 1 + gbase + (unsigned)((rowL >> 5) & 31u);
+          x1 = gop(q1[0], q1[32], u0);
+        }
+        unsigned u1 = 0u;
+        if (fz & 2u) pm += frozen_pen(x1);
+        else u1 = info_leaf(x1);
+        cur = ((small & 1u) ^ u1) | (u1 << 1);
       }
-      __syncwarp();   // forked paths read their parents' slots from here on
       // ------------------------------------------------------------------ partial-sum cascade
-      // z = number of completed right children above leaf i  (polar_scl.py:147-153, [bl ^ br, br])
-      const int z = (i == N - 1) ? M : (__ffs(~i) - 1);
-      uint32_t cur = bit;
+      // z = number of completed right children above leaf i0+1  (polar_scl.py:147-153, [bl ^ br, br]); z >= 1
+      const int z = (i0 + 1 == N - 1) ? M : (__ffs(~(i0 + 1)) - 1);
       const int zs = z < 5 ? z : 5;
-      for (int s = 0; s < zs; ++s) {
-        const uint32_t w = 1u << s;
+      for (int sN = 1; sN < zs; ++sN) {
+        const uint32_t w = 1u << sN;
         const uint32_t field = (small >> (w - 1u)) & ((1u << w) - 1u);
         cur = (field ^ cur) | (cur << w);
       }
@@ -326,15 +363,15 @@ __global__ void __launch_bounds__(32 * WPC, CPS) scl3_kernel(const Params P) {
         const int nwz = 1 << (z - 5);
         uint32_t *dest = ((z < M) ? (bl + (size_t)(nwz - 1) * 32) : rootw) + lane;
         dest[(nwz - 1) * 32] = cur;
-        for (int s = 5; s < z; ++s) {
-          const int hw = 1 << (s - 5);
-          const uint32_t *bls = bl + (size_t)(hw - 1) * 32 + gbase + (unsigned)((rowB >> (5 * s)) & 31u);
+        for (int sN = 5; sN < z; ++sN) {
+          const int hw = 1 << (sN - 5);
+          const uint32_t *bls = bl + (size_t)(hw - 1) * 32 + gbase + (unsigned)((rowB >> (5 * sN)) & 31u);
           for (int w = 0; w < hw; ++w) dest[(nwz - 2 * hw + w) * 32] = bls[w * 32] ^ dest[(nwz - hw + w) * 32];
         }
         if (z < M) rowB = (rowB & ~(31ull << (5 * z))) | ((unsigned long long)p << (5 * z));
         __syncwarp();
       }
-    }  // leaves
+    }  // leaf pairs
 
     // ---------------------------------------------------------------------- epilogue
     // root partial sums = codeword estimate x_hat; u_hat = T(x_hat) (involution); lane-private words
