@@ -520,6 +520,13 @@ int launch_scl3(const float *logit, const uint32_t *fmask, int n, int L, int64_t
     if (ss == 583) return scl3::launch_one<MM, LL, 5, 8, 3>(P, cap, st, plan_only, B);                 \
     if (ss == 5122) return scl3::launch_one<MM, LL, 5, 12, 2>(P, cap, st, plan_only, B);               \
     if (ss == 574) return scl3::launch_one<MM, LL, 5, 7, 4>(P, cap, st, plan_only, B);                 \
+    if (ss == 643) return scl3::launch_one<MM, LL, 6, 4, 3>(P, cap, st, plan_only, B);                 \
+    if (ss == 652) return scl3::launch_one<MM, LL, 6, 5, 2>(P, cap, st, plan_only, B);                 \
+    if (ss == 642) return scl3::launch_one<MM, LL, 6, 4, 2>(P, cap, st, plan_only, B);                 \
+    if (ss == 543) return scl3::launch_one<MM, LL, 5, 4, 3>(P, cap, st, plan_only, B);                 \
+    if (ss == 545) return scl3::launch_one<MM, LL, 5, 4, 5>(P, cap, st, plan_only, B);                 \
+    if (ss == 546) return scl3::launch_one<MM, LL, 5, 4, 6>(P, cap, st, plan_only, B);                 \
+    if (ss == 547) return scl3::launch_one<MM, LL, 5, 4, 7>(P, cap, st, plan_only, B);                 \
     if (ss == 48) return scl3::launch_one<MM, LL, 4, 8, 4>(P, cap, st, plan_only, B);                  \
     if (ss == 416) return scl3::launch_one<MM, LL, 4, 16, 2>(P, cap, st, plan_only, B);                \
     if (ss == 412) return scl3::launch_one<MM, LL, 4, 12, 2>(P, cap, st, plan_only, B);                \
