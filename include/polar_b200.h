@@ -71,7 +71,10 @@ int polar_sc_decode_boxplus_f32(const float *d_logit, const uint32_t *d_frozen_m
  * Replaces SCL_Dec._decode_np_batch and everything under it (x_run_sn_polar/polar/polar_scl.py:49-209),
  * the argmin/gather of forward (:224-228) and, when crc_len > 0, the CRC-aided selection of
  * my_sn/fec/polar/dec.py:507-527 (+ my_sn/fec/crc.py:119-138).  fp64 LLR tree and path metrics,
- * pm += log(1+exp(-x)); lazy copy-on-write of the tree through per-stage pointer tables.
+ * pm += log(1+exp(-x)) evaluated literally; lazy copy-on-write of the tree through per-stage pointer tables.
+ * Two mappings behind the one entry point: csrc/polar_scl3.cu (n in [256,4096], L in [2,32], 16-byte aligned rows:
+ * two virtual top stages computed from the channel row, tree in shared memory) and csrc/polar_scl.cu (everything
+ * else); they return identical bits (tests/test_gpu_parity.py::test_scl3_equals_scl2_lists_and_path_metrics).
  *  L power of two, 1 <= L <= 32; n power of two, 2 <= n <= POLAR_SCL_MAX_N
  *  d_best_packed  [B, POLAR_WORDS(n)] decisions of the selected path
  *  d_u_info_f32   [B, k] fp32 or NULL (as above)
@@ -166,6 +169,10 @@ int polar_count_errors_f32(const float *d_b, const float *d_b_hat, int k, int64_
  *  target_* < 0: rule disabled. */
 int polar_mc_control(unsigned long long *d_delta4, long long *d_state8, long long target_bit_errs,
                      long long target_block_errs, long long max_mc_iter, void *stream);
+
+/* Test hook: d_mismatch3[0..2] += how many of `count` pseudo-random arguments in [-30, 30] make the decoder's own
+ * exp / log / log(1+exp(.)) sequences (csrc/polar_softplus.cuh) differ BITWISE from the CUDA math library's. */
+int polar_scl3_math_selftest(uint64_t count, unsigned long long *d_mismatch3, void *stream);
 
 /* ---- bit (un)packing helpers used by the Python mirror ---------------------------------------- */
 int polar_pack_bits_f32(const float *d_x /*[B,n] 0/1*/, int n, int64_t B, uint32_t *d_packed, void *stream);

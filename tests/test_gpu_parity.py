@@ -237,6 +237,46 @@ def test_scl_matches_oracle_random(n, k, L, B, ebno):
     assert np.array_equal(res["u_info"].cpu().numpy().astype(np.uint8), u_ref[:, 0][:, po.info_positions(fp, n)])
 
 
+def test_scl3_literal_softplus_is_bit_identical_to_the_math_library():
+    """polar_softplus.cuh: exp_nb / log_nb / softplus_literal return the same bits as CUDA's exp / log on [-30, 30]
+    (incl. the clip values and fp32-representable arguments) -- the path-metric arithmetic of scl3 is the
+    reference's literal log(1 + exp(.)), polar_scl.py:82-83."""
+    import ctypes
+    import torch
+    dk = _dk()
+    dev = torch.device("cuda", 0)
+    cnt = torch.zeros(3, dtype=torch.int64, device=dev)
+    fn = dk.lib().polar_scl3_math_selftest
+    fn.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
+    dk.check(fn(1 << 26, dk.ptr(cnt), dk.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    assert cnt.tolist() == [0, 0, 0]
+
+
+@pytest.mark.parametrize("n,L,B,ebno", [(256, 4, 8192, 2.0), (512, 16, 2048, 3.0), (1024, 8, 8192, 3.0), (1024, 2, 4099, 4.0),
+                                        (2048, 32, 515, 3.5), (4096, 8, 1024, 4.0)])
+def test_scl3_equals_scl2_lists_and_path_metrics(n, L, B, ebno, monkeypatch):
+    """The two SCL mappings (polar_scl3.cu: virtual top stages, pair loop; polar_scl.cu scl2_kernel: everything
+    stored) must return identical bits: best path, the whole sorted list and every path metric (bit-exact, not rtol),
+    also for ragged batches (B not a multiple of the codewords per warp / CTA)."""
+    import torch
+    from oracle import polar_oracle as po
+    dk = _dk()
+    k = n // 2
+    dev = torch.device("cuda", 0)
+    fp = po.rm_frozen_pos(n, n - k)
+    tables = dk.code_tables(fp, n, dev)
+    _, _, x = dk.awgn_frontend(tables, B, po.ebnodb2no(ebno, 2, k / n), 99 + n + L)
+    out = {}
+    for mode in ("1", "2"):
+        monkeypatch.setenv("POLAR_SCL_MODE", mode)
+        out[mode] = dk.scl_decode(x, tables, L, want_packed=True, want_info=True, want_pm=True, want_list=True)
+        torch.cuda.synchronize()
+    for key in ("u_packed", "u_info", "list"):
+        assert torch.equal(out["1"][key], out["2"][key]), key
+    assert torch.equal(out["1"]["pm"].view(torch.int64), out["2"]["pm"].view(torch.int64))
+
+
 def test_scl_api_errors_and_shapes():
     import torch
     from polar.polar_scl import SCL_Dec
