@@ -62,6 +62,7 @@ _SIGNATURES = {
   "polar_count_errors_packed": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
   "polar_count_errors_f32": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp]),
   "polar_mc_control": (_i32, [_vp, _vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _vp]),
+  "polar_scl3_math_selftest": (_i32, [ctypes.c_uint64, _vp, _vp]),
   "polar_pack_bits_f32": (_i32, [_vp, _i32, _i64, _vp, _vp]),
   "polar_unpack_info_f32": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp]),
   "polar_sc_decode_host": (_i32, [_vp, _vp, _i32, _i64, _vp, _i32]),

@@ -247,7 +247,6 @@ def test_scl3_literal_softplus_is_bit_identical_to_the_math_library():
     dev = torch.device("cuda", 0)
     cnt = torch.zeros(3, dtype=torch.int64, device=dev)
     fn = dk.lib().polar_scl3_math_selftest
-    fn.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
     dk.check(fn(1 << 26, dk.ptr(cnt), dk.stream_ptr(dev)))
     torch.cuda.synchronize()
     assert cnt.tolist() == [0, 0, 0]

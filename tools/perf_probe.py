@@ -119,7 +119,6 @@ def main():
         import ctypes
         cnt = torch.zeros(3, dtype=torch.int64, device=dev)
         N = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 28
-        dk.lib().polar_scl3_math_selftest.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
         dk.check(dk.lib().polar_scl3_math_selftest(N, dk.ptr(cnt), dk.stream_ptr(dev)))
         torch.cuda.synchronize()
         print("softplus selftest: %d arguments, mismatches exp/log/softplus vs CUDA math library:" % N, cnt.tolist(), flush=True)
