@@ -28,6 +28,10 @@
 
 namespace polar {
 
+#ifndef POLAR_SCL3_RANK
+#define POLAR_SCL3_RANK 1
+#endif
+
 namespace scl3 {
 
 constexpr double kLlrMaxD = 30.0;
@@ -75,7 +79,13 @@ struct Cfg {
   static constexpr int HT = 1 << TOP;                     // elements per pass
   static constexpr int CPW = 32 / L;
   static constexpr int LOGL = Log2<L>::v;
-  static constexpr size_t smem_bytes = (size_t)32 * 8 * ((1u << SS) - 1u);
+  static constexpr size_t llr_smem_bytes = (size_t)32 * 8 * ((1u << SS) - 1u);
+  // ranking scratch (L <= 8): candidate keys [group][L+1] x 16 B (one pad entry per group: conflict-free broadcast
+  // reads), then the survivors [group][L+1] x 16 B
+  static constexpr bool RANK = (L <= 8) && (POLAR_SCL3_RANK != 0);
+  static constexpr int GSTRIDE = L + 1;                        // 16-byte entries per lane group
+  static constexpr size_t rank_bytes = RANK ? (size_t)2 * CPW * GSTRIDE * 16 : 0;
+  static constexpr size_t smem_bytes = llr_smem_bytes + rank_bytes;
   static constexpr size_t gl_doubles = (size_t)32 * ((1u << (TOP + 1)) - (1u << SS));
   static constexpr size_t word_count = (size_t)32 * 2 * NW;
   static constexpr size_t ws_bytes = ((gl_doubles * 8 + word_count * 4 + 255) / 256) * 256;
@@ -289,6 +299,30 @@ __global__ void __launch_bounds__(32 * WPC, CPS) scl3_kernel(const Params P) {
         const double xc = fmax(fmin(x, kLlrMaxD), -kLlrMaxD);     // polar_scl.py:81
         double k0 = pm + sp::softplus_literal(-xc), k1 = pm + sp::softplus_literal(xc);   // u = 0 / u = 1
         int s0 = p, s1 = L + p;
+        if constexpr (C::RANK) {
+          // rank by counting: every candidate is compared with all 2L candidates of its codeword (independent
+          // compares instead of the 3 log2(2L) dependent shuffle layers of a sorting network); ties go to the lower
+          // candidate index, like the stable sort.  rank < L survives and moves to lane `rank` of the group.
+          double2 *kb = reinterpret_cast<double2 *>(reinterpret_cast<unsigned char *>(llr_s) + C::llr_smem_bytes) + cwl * C::GSTRIDE;
+          kb[p] = make_double2(k0, k1);
+          __syncwarp();
+          int r0 = 0, r1 = 0;
+#pragma unroll
+          for (int j = 0; j < L; ++j) {
+            const double2 o = kb[j];
+            const bool jl = j < p;
+            r0 += (int)((o.x < k0) || (o.x == k0 && jl));
+            r0 += (int)(o.y < k0);
+            r1 += (int)(o.x <= k1);
+            r1 += (int)((o.y < k1) || (o.y == k1 && jl));
+          }
+          double2 *sb = kb + CPW * C::GSTRIDE;                     // survivors of this group
+          if (r0 < L) sb[r0] = make_double2(k0, __hiloint2double(0, s0));
+          if (r1 < L) sb[r1] = make_double2(k1, __hiloint2double(0, s1));
+          __syncwarp();
+          const double2 w = sb[p];
+          k0 = w.x; s0 = __double2loint(w.y);
+        } else {
 #pragma unroll
         for (int k = 2; k <= 2 * L; k <<= 1) {
 #pragma unroll
@@ -308,6 +342,7 @@ __global__ void __launch_bounds__(32 * WPC, CPS) scl3_kernel(const Params P) {
               if ((lower == up1) == less1) { k1 = pk1; s1 = ps1; }
             }
           }
+        }
         }
         const int parent = gbase + (s0 & (L - 1));
         pm = k0;
