@@ -96,7 +96,16 @@ extern "C" int polar_scl_decode_host(const float *h_logit, const uint32_t *h_fro
   for (int i = 0; i < 2; ++i)
     if (!C.st[i]) POLAR_CUDA(cudaStreamCreateWithFlags(&C.st[i], cudaStreamNonBlocking));
   const int nw = POLAR_WORDS(n);
-  const int64_t chunk = chunk_codewords(n, B);
+  int64_t chunk = chunk_codewords(n, B);
+  if (scl3_supported(n, L) && chunk < B) {
+    // the list kernel is persistent: every resident warp decodes the same number of 32/L-codeword groups, so a chunk
+    // should be a whole number of such rounds (a 128 MB chunk of n = 1024 is 3.46 rounds: 13 % of the last one idle)
+    Scl3Plan p3;
+    if (launch_scl3(nullptr, nullptr, n, L, B, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, &p3) == POLAR_OK) {
+      const int64_t round = p3.grid * (32 / L);
+      if (round > 0 && chunk > round) chunk = chunk / round * round;
+    }
+  }
   const size_t ws_need = polar_scl_workspace_bytes(n, L, chunk);
   int rc;
   if ((rc = grow2(C.logit, &C.logit_bytes, (size_t)chunk * n * 4))) return rc;

@@ -31,6 +31,9 @@ namespace polar {
 #ifndef POLAR_SCL3_RANK
 #define POLAR_SCL3_RANK 1
 #endif
+#ifndef POLAR_SCL3_RANK_MAXL
+#define POLAR_SCL3_RANK_MAXL 16
+#endif
 
 namespace scl3 {
 
@@ -82,7 +85,7 @@ struct Cfg {
   static constexpr size_t llr_smem_bytes = (size_t)32 * 8 * ((1u << SS) - 1u);
   // ranking scratch (L <= 8): candidate keys [group][L+1] x 16 B (one pad entry per group: conflict-free broadcast
   // reads), then the survivors [group][L+1] x 16 B
-  static constexpr bool RANK = (L <= 8) && (POLAR_SCL3_RANK != 0);
+  static constexpr bool RANK = (L <= POLAR_SCL3_RANK_MAXL) && (POLAR_SCL3_RANK != 0);
   static constexpr int GSTRIDE = L + 1;                        // 16-byte entries per lane group
   static constexpr size_t rank_bytes = RANK ? (size_t)2 * CPW * GSTRIDE * 16 : 0;
   static constexpr size_t smem_bytes = llr_smem_bytes + rank_bytes;
