@@ -269,6 +269,7 @@ def main():
                "matches_device_path": ok}
         del h_logits, h_out
 
+    peaks, peak_src = measured_peaks()
     # ---- SCL L=8 + CRC11 (configs[2]) ------------------------------------------------------------------
     scl = None
     if not args.skip_scl:
@@ -318,7 +319,14 @@ def main():
         c = cnt.cpu().numpy()
         scl = {"metric": "decoded_info_throughput_scl8_crc11_n1024", "value": scl_cws * k / 1e9, "unit": "Gbit/s",
                "codewords_per_s": scl_cws, "ms_per_step": scl_ms, "batch": Bs, "ebno_db": SCL_EBNO_DB,
-               "bler": float(c[1]) / Bs, "workload": "SCL L=8 k=512 (501+CRC11) n=1024 CRC-aided selection, batch 256K (configs[2])"}
+               "bler": float(c[1]) / Bs, "workload": "SCL L=8 k=512 (501+CRC11) n=1024 CRC-aided selection, batch 256K (configs[2])",
+               "kernel": "scl3_kernel<10,8,5,4,4> (polar_scl3.cu)",
+               "roofline": {"bound": "hbm", "achieved": scl_cws / world * (4 * n + k / 8) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": scl_cws / world * (4 * n + k / 8) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                            "note": "algorithmic bytes (4n + k/8 per codeword) are irrelevant for the list decoder: 98 k warp "
+                                    "instructions per codeword (fp64 tree for 8 paths, literal log(1+exp) metric, rank of 16 "
+                                    "candidates per information bit); bound by per-warp latency at 58 % issue utilisation, "
+                                    "no pipe above 43 % (profiles/r01_scl3_kernel_ncu.md, DESIGN.md 4.2)"}}
         if not args.skip_e2e:
             h_lg = torch.empty((Bs, n), dtype=torch.float32, pin_memory=True)
             h_lg.copy_(lg)
@@ -349,7 +357,6 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    peaks, peak_src = measured_peaks()
     bytes_per_cw = 4 * n + k // 8           # fp32 logits in, bit-packed decisions out (k info bits)
     achieved = B * bytes_per_cw / (kern_ms * 1e-3) / 1e9
     cpu = None
