@@ -16,6 +16,8 @@
 //     storage); stages 7 and 6 plus the partial-sum words in shared memory (916 B per codeword).
 //   * only partial sums are produced on the serial path; the decisions are recovered once per codeword as
 //     u = T(x_hat).
+#include <mutex>
+
 #include "polar_common.cuh"
 #include "polar_internal.h"
 
@@ -34,6 +36,8 @@ constexpr unsigned FULLMASK = 0xFFFFFFFFu;
       const long long t__ = clock64(); g_sc4_dbg[slot] += (unsigned long long)(t__ - tlast); tlast = t__; \
     }                                                                                 \
   } while (0)
+
+constexpr size_t kSc4ScratchPerSm = (size_t)512 * 1024;   // 8 warps x 32 codewords x 512 floats (n=1024) = 4 x 32 x 1024 (n=2048)
 
 struct Sc4Layout {
   int nw, nws, n64, top, stride;
@@ -68,6 +72,17 @@ PDEV uint64_t l2_policy_evict_first() {
 }
 PDEV uint64_t l2_policy_evict_normal() {
   uint64_t p; asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+// coherent 128-bit load / store with an L2 eviction policy (the stage scratch is written and read by the same kernel)
+PDEV float4 ldg4_coh_hint(const float *p, uint64_t policy) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy) : "memory");
+  return v;
+}
+PDEV void stg4_hint(float *p, const float4 v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy) : "memory");
 }
 PDEV float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 PDEV void sts4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
@@ -182,21 +197,31 @@ __device__ __noinline__ void step_glob(const float *__restrict__ logit, int64_t 
 // kind = quarter of the codeword the target node covers: 0 LL, 1 LR, 2 RL, 3 RR (warp-uniform).
 // Work item p = lane + 32k = (codeword c, pair q): the float4 at elements 4q and 4q + H/2 of the stage M-2
 // node, i.e. exactly what one f/g of the next step consumes; it goes to TMEM columns 8k..8k+7 of the lane.
-template <int M>
+// scr (optional): per-warp global scratch [32 codewords][N/2 floats] that stays in the L2.  The passes that compute a
+// LEFT stage M-2 node (kind 0 / 2) also store the stage M-1 node they had to form; the pass for its right sibling
+// (kind 1 / 3, a quarter of a decode later) then reads those N/2 values instead of the whole channel row again and
+// skips two of its three f/g per element.  scr_load is only set when the left pass of this batch really ran (it is
+// skipped when the left node is rate-0).
+template <int M, bool STORE>
 __device__ __noinline__ void step_virt_tmem(const int kind, const float *__restrict__ logit, int64_t cw0, int nvalid,
-                                            const uint32_t *beta, int nws, int lane, uint32_t tm_base, int hints) {
+                                            const uint32_t *beta, int nws, int lane, uint32_t tm_base, int hints,
+                                            float *scr) {
   constexpr int N = 1 << M, H = N >> 2, PQ = H >> 3, HW = H >> 5;   // PQ pairs per codeword (multiple of 32)
   constexpr int KMAX = PQ;                                          // 32 codewords * PQ pairs / 32 lanes
   constexpr int VU = 2;                                             // pairs per round; rounds are double buffered
   // The row is read four times, a quarter of the decode apart, and the rows in flight (148 SMs x 8 warps x 32 x 4 KB)
   // exceed the L2.  hints = 1: keep every row until its last pass (evict_last x3, evict_first).  hints = 2: only protect
   // the pairs of passes that are a quarter apart (0->1 and 2->3), halving the protected set so that it fits.
-  const uint64_t pol = !hints ? l2_policy_evict_normal()
+  // With the stage scratch (STORE) the sibling pass does not come back to the row: stream it (evict_first) and leave
+  // the L2 to the scratch.
+  const uint64_t pol = STORE ? l2_policy_evict_first()
+                     : !hints ? l2_policy_evict_normal()
                      : (hints == 2) ? ((kind & 1) ? l2_policy_evict_first() : l2_policy_evict_last())
                                     : ((kind == 3) ? l2_policy_evict_first() : l2_policy_evict_last());
   const bool right = kind >= 2, is_g = kind & 1;
   const int gw = (kind == 3) ? 2 * HW : 0;
   float4 c0[2][VU][2], c1[2][VU][2], c2[2][VU][2], c3[2][VU][2];      // [buffer][pair][element]
+  constexpr bool scr_store = STORE;
   auto issue = [&](int buf, int k0) {
 #pragma unroll
     for (int r = 0; r < VU; ++r) {
@@ -229,6 +254,11 @@ __device__ __noinline__ void step_virt_tmem(const int kind, const float *__restr
         } else {                   // right half: stage M-1 node = g(channel, beta of the left half)
           y0 = g4neg(c0[buf][r][e], c2[buf][r][e], bw[0] >> sh); y1 = g4neg(c1[buf][r][e], c3[buf][r][e], bw[HW] >> sh);
         }
+        if constexpr (scr_store) {
+          float *sp = scr + c * (2 * H) + j;
+          const uint64_t pol_scr = l2_policy_evict_last();
+          stg4_hint(sp, y0, pol_scr); stg4_hint(sp + H, y1, pol_scr);
+        }
         if (!is_g) o[e] = f4(y0, y1);
         else o[e] = g4(y0, y1, bw[gw] >> sh);
       }
@@ -243,6 +273,50 @@ __device__ __noinline__ void step_virt_tmem(const int kind, const float *__restr
     compute(0, k0);
     if (k0 + 2 * VU < KMAX) issue(0, k0 + 2 * VU);
     compute(1, k0 + VU);
+  }
+  tmem_wait_st();
+}
+
+// The right-sibling pass (kind 1 / 3) when the left pass of this batch stored the stage M-1 node: one g per element
+// from N/2 scratch values per codeword instead of three f/g from the whole channel row.
+template <int M>
+__device__ __noinline__ void step_virt_scr(const int kind, const uint32_t *beta, int nws, int lane, uint32_t tm_base,
+                                           const float *scr, const bool discard) {
+  constexpr int N = 1 << M, H = N >> 2, PQ = H >> 3, HW = H >> 5;
+  constexpr int KMAX = PQ, VU = 4;
+  const uint64_t pol = l2_policy_evict_last();
+  const int gw = (kind == 3) ? 2 * HW : 0;
+#pragma unroll 1
+  for (int k0 = 0; k0 < KMAX; k0 += VU) {
+    float4 a[VU][2], b[VU][2];
+#pragma unroll
+    for (int r = 0; r < VU; ++r) {
+      const int p = lane + 32 * (k0 + r);
+      const int c = (int)((unsigned)p / (unsigned)PQ), q = (int)((unsigned)p % (unsigned)PQ);
+      const float *sp = scr + c * (2 * H) + 4 * q;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) { a[r][e] = ldg4_coh_hint(sp + e * (H / 2), pol); b[r][e] = ldg4_coh_hint(sp + e * (H / 2) + H, pol); }
+    }
+#pragma unroll
+    for (int r = 0; r < VU; ++r) {
+      const int p = lane + 32 * (k0 + r);
+      const int c = (int)((unsigned)p / (unsigned)PQ), q = (int)((unsigned)p % (unsigned)PQ);
+      float4 o[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = 4 * q + e * (H / 2);
+        o[e] = g4(a[r][e], b[r][e], beta[c * nws + (j >> 5) + gw] >> (j & 31));
+      }
+      tmem_st8(tm_base + 8 * (k0 + r), o[0], o[1]);
+      if (discard && (lane & 7) == 0) {      // the 8 lanes of a 128-byte line have consumed it: drop it from the L2 unwritten
+        const float *sp = scr + c * (2 * H) + 4 * q;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          asm volatile("discard.global.L2 [%0], 128;" ::"l"(sp + e * (H / 2)) : "memory");
+          asm volatile("discard.global.L2 [%0], 128;" ::"l"(sp + e * (H / 2) + H) : "memory");
+        }
+      }
+    }
   }
   tmem_wait_st();
 }
@@ -379,7 +453,7 @@ PDEV uint4 bottom128(const float *node, uint64_t fm0, uint64_t fm1) {
 template <int M, int MODE>
 __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ logit, const uint32_t *__restrict__ fmask_g,
                                                      int64_t B, int64_t nbatches, int l2_prefetch, int l2_hints, int dbg,
-                                                     uint32_t *__restrict__ u_packed, float *__restrict__ u_info,
+                                                     float *scratch, int scr_discard, uint32_t *__restrict__ u_packed, float *__restrict__ u_info,
                                                      const int32_t *__restrict__ info_pos, int k) {
   constexpr bool TM = MODE >= 1, VIRT = MODE == 2;
   constexpr int TS = VIRT ? M - 2 : M - 1;                  // stage held in tensor memory (TM only)
@@ -424,6 +498,15 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
     for (int idx = N64 - 1; idx >= 1; --idx) nz[idx] = nz[2 * idx] & nz[2 * idx + 1];
   __syncthreads();
 
+  // stage scratch of this warp: indexed by the PHYSICAL SM (only one CTA of this kernel fits on an SM, so concurrent
+  // launches on other streams can never share a slot), kSc4ScratchPerSm bytes per SM.  Recomputed at each use: the
+  // 128-leaf subtrees need every register, nothing extra may stay live across them.
+  auto scr_ptr = [&]() -> float * {
+    if (!VIRT || !scratch) return nullptr;
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    return scratch + (size_t)smid * (kSc4ScratchPerSm / 4) + (size_t)(threadIdx.x >> 5) * (32 * (N / 2));
+  };
   long long tlast = clock64();
   const long long tstart = tlast;
   const int64_t wstride = (int64_t)gridDim.x * nwarps;
@@ -452,7 +535,11 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
         // g step into (S, i) from its parent at stage S+1; the left sibling's beta starts at word 2*(i - 2^(S-6))
         const int left_word = WB * (i - (1 << (S - BOT)));
         if (VIRT && S == M - 2) {
-          step_virt_tmem<M>(i < N64 / 2 ? 1 : 3, logit, cw0, nvalid, beta, NWS, lane, tm_base, l2_hints);
+          // the left sibling's pass stored its stage M-1 node unless it was skipped (left quarter rate-0)
+          const int kind = i < N64 / 2 ? 1 : 3;
+          float *scr = scr_ptr();
+          if (scr && !nz[4 + kind - 1]) step_virt_scr<M>(kind, beta, NWS, lane, tm_base, scr, scr_discard != 0);
+          else step_virt_tmem<M, false>(kind, logit, cw0, nvalid, beta, NWS, lane, tm_base, l2_hints, nullptr);
         } else if (TM && !VIRT && S == M - 1) {
           step_glob_tmem<M, true>(logit, cw0, nvalid, beta, NWS, lane, tm_base);
         } else if (TM && S == TS - 1) {
@@ -469,7 +556,11 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
         if (nz[(N64 >> (s - 1 - BOT)) + (i >> (s - 1 - BOT))]) { zeroed = true; --s; break; }   // left child is rate-0
         if (VIRT && s == M) { --s; continue; }                                         // virtual stage: nothing stored
         if (VIRT && s == M - 1) {
-          step_virt_tmem<M>(i < N64 / 2 ? 0 : 2, logit, cw0, nvalid, beta, NWS, lane, tm_base, l2_hints);
+          {
+            float *scr = scr_ptr();
+            if (scr) step_virt_tmem<M, true>(i < N64 / 2 ? 0 : 2, logit, cw0, nvalid, beta, NWS, lane, tm_base, l2_hints, scr);
+            else step_virt_tmem<M, false>(i < N64 / 2 ? 0 : 2, logit, cw0, nvalid, beta, NWS, lane, tm_base, l2_hints, nullptr);
+          }
         } else if (TM && !VIRT && s == M) {
           step_glob_tmem<M, false>(logit, cw0, nvalid, beta, NWS, lane, tm_base);
         } else if (TM && s == TS) {
@@ -560,6 +651,35 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
   }
 }
 
+__global__ void nsmid_kernel(unsigned *out) {
+  unsigned v;
+  asm volatile("mov.u32 %0, %%nsmid;" : "=r"(v));
+  *out = v;
+}
+// Per-device stage scratch of the virtual-stage kernels (n >= 1024), allocated on first use and kept for the life of
+// the process: %nsmid slots of kSc4ScratchPerSm (76 MB on a 148-SM part) -- small enough to stay resident in the L2.
+float *sc4_scratch() {
+  static std::mutex mu;
+  static float *buf[64];
+  static bool tried[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!tried[dev]) {
+    tried[dev] = true;
+    unsigned *d_n = nullptr, h_n = 0;
+    if (cudaMalloc(&d_n, sizeof(unsigned)) == cudaSuccess) {
+      nsmid_kernel<<<1, 1>>>(d_n);
+      if (cudaMemcpy(&h_n, d_n, sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) h_n = 0;
+      cudaFree(d_n);
+    }
+    void *p = nullptr;
+    if (h_n > 0 && h_n <= 1024 && cudaMalloc(&p, (size_t)h_n * kSc4ScratchPerSm) == cudaSuccess) buf[dev] = (float *)p;
+    else (void)cudaGetLastError();
+  }
+  return buf[dev];
+}
+
 template <int M, int MODE>
 int launch_sc4_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t *u_packed, float *u_info,
                  const int32_t *info_pos, int k, int warps, cudaStream_t st) {
@@ -585,8 +705,9 @@ int launch_sc4_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t 
   int64_t grid = (nbatches + warps - 1) / warps;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
+  float *scratch = (MODE == 2 && env_int("POLAR_SC4_SCRATCH", 1)) ? sc4_scratch() : nullptr;
   kern<<<(unsigned)grid, warps * 32, smem, st>>>(logit, fmask, B, nbatches, env_int("POLAR_SC4_PREFETCH", 0),
-                                                  env_int("POLAR_SC4_HINTS", 2), env_int("POLAR_SC3_DBG", 0), u_packed, u_info, info_pos, k);
+                                                  env_int("POLAR_SC4_HINTS", 2), env_int("POLAR_SC3_DBG", 0), scratch, env_int("POLAR_SC4_DISCARD", 1), u_packed, u_info, info_pos, k);
   count_launch();
   POLAR_CHECK_LAUNCH("sc4_kernel");
   return POLAR_OK;
