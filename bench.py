@@ -381,9 +381,11 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
                      "kernel": "sc4_kernel<10,2> (polar_sc4.cu)", "kernel_ms": kern_ms, "bytes_per_codeword": bytes_per_cw,
-                     "note": "algorithmic bytes = 4n + k/8 per codeword; the kernel re-reads the channel row 4x (virtual stage m-1), "
-                             "so DRAM traffic is ~2.9x the algorithmic bytes (profiles/); binding bounds are the ALU-pipe issue rate "
-                             "of the serial SC chains and DRAM bandwidth of the re-reads (DESIGN.md 4.1)"},
+                     "note": "algorithmic bytes = 4n + k/8 per codeword; stage m-1 is virtual: the channel row is read twice "
+                             "(once per half of the codeword), the two sibling passes in between read an L2-resident stage "
+                             "scratch instead, so DRAM traffic is ~2.0x the algorithmic bytes (profiles/; 2.9x before the "
+                             "scratch); binding bounds are the issue rate of the serial SC chains (128-leaf subtrees, 2 warps "
+                             "per scheduler) and DRAM bandwidth of the row passes (DESIGN.md 4.1)"},
         "cpu_baseline": cpu, "parity": parity, "scl8": scl,
     }
     print(json.dumps(line), flush=True)

@@ -11,7 +11,10 @@
  *  - Every pointer named d_* is a DEVICE pointer into caller-owned memory (e.g. a torch CUDA
  *    tensor's data_ptr()); h_* is a HOST pointer.  No torch types cross this boundary.
  *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device entry
- *    points only enqueue work: they never synchronise and never allocate.
+ *    points only enqueue work: they never synchronise and never allocate -- with one exception: the first SC
+ *    decode of n >= 1024 on a device allocates that device's stage scratch (one slot per SM, 76 MB on a 148-SM
+ *    part, kept for the life of the process; csrc/polar_sc4.cu).  If that allocation is impossible (e.g. during
+ *    stream capture) the kernel runs without the scratch.
  *  - Bit packing: bit (i % 32) of 32-bit word (i / 32) holds position i (LSB first); a row of n
  *    positions occupies POLAR_WORDS(n) = max(1, n/32) words.
  *  - Logits follow the reference decoder input: ln P(1)/P(0), fp32, row-major [B, n]
