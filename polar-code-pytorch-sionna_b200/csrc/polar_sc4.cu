@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
       // node entered at block i: the root, or the right child whose left sibling just finished
       const int S = (i == 0) ? M : BOT + (__ffs(i) - 1);
       int s = S;
-      if (VIRT && l2_prefetch && ((i + 1) & (N64 / 4 - 1)) == 0) {
+      if (VIRT && l2_prefetch && ((i + 1) & ((l2_prefetch == 2 ? N64 / 2 : N64 / 4) - 1)) == 0) {
         // the block after this one starts with a pass over the channel rows (this batch's next quarter, or the next
         // batch's first): ask the L2 for them now, one 64-leaf.. block (several microseconds) ahead of the loads
         const int64_t pb = (i + 1 < N64) ? batch : batch + wstride;
