@@ -31,6 +31,9 @@ namespace polar {
 #ifndef POLAR_SCL3_RANK
 #define POLAR_SCL3_RANK 1
 #endif
+#ifndef POLAR_SCL3_DISCARD
+#define POLAR_SCL3_DISCARD 1
+#endif
 #ifndef POLAR_SCL3_RANK_MAXL
 #define POLAR_SCL3_RANK_MAXL 16
 #endif
@@ -170,6 +173,15 @@ __global__ void __launch_bounds__(32 * WPC, CPS) scl3_kernel(const Params P) {
           for (int r = 0; r < 8; ++r) dst[(w * 32 + e0 + r) * 32] = gop(a[r], b[r], (ub >> (e0 + r)) & 1u);
         }
       }
+    }
+    if constexpr (T + 1 >= SS && POLAR_SCL3_DISCARD) {
+      // every path has now consumed stage T+1 for the last time (it is rewritten before it is read again): drop the
+      // array from the L2 instead of letting its dirty lines be written back to DRAM
+      __syncwarp();
+      const char *dead = reinterpret_cast<const char *>(stage_gl(std::integral_constant<int, T + 1>{}));
+#pragma unroll 1
+      for (int ln = lane; ln < (2 << (T + 1)); ln += 32)
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(dead + (size_t)ln * 128) : "memory");
     }
   };
   // one pass of the virtual top: stage TOP of this path from the channel row.  Q = (i >> TOP): bit 2 / 1 / 0
