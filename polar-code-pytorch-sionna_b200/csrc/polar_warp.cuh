@@ -62,12 +62,18 @@ struct Philox {
 };
 
 // Box-Muller: two uint32 -> two independent N(0,1).
+// Special-function-unit version: lg2 / sqrt / sin / cos are one MUFU instruction each (lg2.approx: 2^-22 relative,
+// sin/cos.approx: 2^-20.9 absolute on [0, 2pi]) instead of ~55 instructions for logf + sqrtf + sincospif -- the front end
+// was bound by instruction issue (1.7 TB/s of logits), and errors of 1e-6 in a noise sample are far below anything a
+// Monte-Carlo BER estimate resolves (tests/test_gpu_link.py checks mean, variance, kurtosis, tail mass, I/Q correlation).
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   const float u1 = ((float)a + 0.5f) * 2.3283064365386963e-10f;   // (0,1]; float rounding may give 1.0 -> r=0, fine
-  const float u2 = (float)b * 2.3283064365386963e-10f;            // [0,1]
-  const float r = sqrtf(-2.0f * logf(fminf(fmaxf(u1, 1.1754944e-38f), 1.0f)));
-  float s, c;
-  sincospif(2.0f * u2, &s, &c);
+  const float th = (float)b * (2.3283064365386963e-10f * 6.283185307179586f);   // [0, 2pi]
+  float l2, r, s, c;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(l2 * -1.3862943611198906f, 0.0f)));   // -2 ln u1
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(th));
   return make_float2(r * c, r * s);
 }
 
