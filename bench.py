@@ -47,6 +47,44 @@ def frozen_set(n, k):
     return po.rm_frozen_pos(n, n - k)
 
 
+_FULL_AFFINITY = None
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Several ranks per host: run this rank (and first-touch its pinned staging buffers) on the CPU socket the GPU's PCIe
+    root hangs off, so the end-to-end leg of every rank streams from local DRAM.  Best effort; returns the node or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = None
+        if all(hasattr(pr, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        if bdf is None:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
+            bdf = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+            bdf = bdf.decode() if isinstance(bdf, bytes) else bdf
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]                                            # nvml prints an 8-digit PCI domain, sysfs 4
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -107,6 +145,8 @@ def cpu_oracle_rate(kind, logits_np, frozen, L=0, seconds_hint=10.0):
     """Time the C oracle (all host threads) on a bounded sample; returns (cw/s, threads, n_codewords)."""
     from oracle import c_oracle as co
     co.build()
+    if _FULL_AFFINITY and hasattr(os, "sched_setaffinity"):
+        os.sched_setaffinity(0, _FULL_AFFINITY)             # the CPU leg uses every host core again (see bind_to_gpu_numa_node)
     thr = co.num_threads()
     t0 = time.perf_counter()
     if kind == "sc":
@@ -177,6 +217,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    global _FULL_AFFINITY
+    _FULL_AFFINITY = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         # stdout carries exactly one JSON line: NCCL prints its version banner (and NCCL_DEBUG output) to fd 1 while the
         # communicator is created, so fd 1 points at stderr until the first collective is through
@@ -388,7 +431,8 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "SC k=512 n=1024 RM-rule code, AWGN BPSK Eb/N0=4dB, batch %d codewords per GPU (configs[1])" % B,
                    "l2": "inputs (%.1f GiB per GPU) larger than L2, no flush needed" % (B * n * 4 / 2 ** 30),
-                   "parallelism": "batch sharded over %d rank(s), no data-path collective" % world},
+                   "parallelism": "batch sharded over %d rank(s), no data-path collective" % world,
+                   "numa_node_rank0": numa},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
