@@ -421,10 +421,25 @@ def main():
         cpu = {"value": rate * k / 1e9, "unit": "Gbit/s", "codewords_per_s": rate, "cores": thr, "kind": "port",
                "sample": "first %d codewords of the GPU batch, C restatement of the reference (oracle/polar_oracle.c); "
                          "the Python reference itself measured 3270 cw/s on 8 vCPU (BASELINE.md)" % cnt_cw}
+    # the other two candidate bounds next to HBM.  Instruction counts are static (ncu, profiles/), rates live.
+    sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    cw_rate_gpu = B / (kern_ms * 1e-3)
+    WARP_INSTR_PER_CW = 1515.5          # smsp__inst_executed.sum / 2^20 codewords (profiles/r01_sc4_kernel_ncu.md)
+    issue_peak = sms * 4 * sm_clk * 1e6  # one warp instruction per scheduler and cycle
+    other_bounds = {
+        "issue": {"achieved": cw_rate_gpu * WARP_INSTR_PER_CW, "peak": issue_peak, "unit": "warp-instr/s",
+                  "frac": cw_rate_gpu * WARP_INSTR_PER_CW / issue_peak,
+                  "note": "%.1f warp instructions per codeword (ncu); serial SC chains, 2 warps per scheduler" % WARP_INSTR_PER_CW},
+        "dram_actual": {"achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
+                        "note": "filled from roofline.traffic below: bytes the kernel really moves / kernel time"}}
     traffic = None
     tp = os.path.join(ROOT, "profiles", "sc_traffic_bytes_per_launch.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        if traffic and B == (1 << 20):
+            other_bounds["dram_actual"].update(achieved=traffic / (kern_ms * 1e-3) / 1e9,
+                                               frac=traffic / (kern_ms * 1e-3) / 1e9 / peaks["hbm_gbs"])
     line = {
         "metric": "decoded_info_throughput_sc_n1024", "value": value, "unit": "Gbit/s", "codewords_per_s": cws,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -437,6 +452,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
                      "kernel": "sc4_kernel<10,2> (polar_sc4.cu)", "kernel_ms": kern_ms, "bytes_per_codeword": bytes_per_cw,
+                     "other_bounds": other_bounds,
                      "note": "algorithmic bytes = 4n + k/8 per codeword; stage m-1 is virtual: the channel row is read twice "
                              "(once per half of the codeword), the two sibling passes in between read an L2-resident stage "
                              "scratch instead, so DRAM traffic is ~2.0x the algorithmic bytes (profiles/; 2.9x before the "
