@@ -660,11 +660,15 @@ extern "C" size_t polar_scl_workspace_bytes(int n, int L, int64_t B) {
   const SclPlan pl = scl_plan(n, L, B);
   size_t need = (size_t)pl.grid * pl.warps_per_cta * pl.ws_doubles_per_warp * sizeof(double);
 #if !defined(POLAR_F_BOXPLUS)
-  if (scl_mode() == 2 && scl3_supported(n, L)) {   // the larger of the two mappings: misaligned rows fall back to scl2
+  if (scl_mode() == 2 && scl3_supported(n, L)) {
+    // scl3 is what runs; rows that are not 16-byte aligned fall back to scl2, which shrinks its grid to the workspace it
+    // is given (at least one CTA per SM), so its much larger default appetite (1.3 GB at n=1024, L=8) is not reserved
     Scl3Plan p3;
     if (launch_scl3(nullptr, nullptr, n, L, B, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, &p3) == POLAR_OK) {
       const size_t n3 = (size_t)p3.grid * p3.ws_bytes_per_warp;
-      if (n3 > need) need = n3;
+      size_t floor2 = (size_t)device_sm_count() * pl.warps_per_cta * pl.ws_doubles_per_warp * sizeof(double);
+      if (floor2 > need) floor2 = need;
+      need = n3 > floor2 ? n3 : floor2;
     }
   }
 #endif
@@ -696,11 +700,17 @@ extern "C" int polar_scl_decode(const float *d_logit, const uint32_t *d_frozen_m
                        d_crc_rows, crc_len, d_workspace, (cudaStream_t)stream, nullptr);
   }
 #endif
-  const SclPlan pl = scl_plan(n, L, B);
-  const size_t need = (size_t)pl.grid * pl.warps_per_cta * pl.ws_doubles_per_warp * sizeof(double);
+  SclPlan pl = scl_plan(n, L, B);
+  const size_t per_cta = (size_t)pl.warps_per_cta * pl.ws_doubles_per_warp * sizeof(double);
+  const size_t need = (size_t)pl.grid * per_cta;
   if (need > 0) {
-    if (!d_workspace || workspace_bytes < need) return set_error(POLAR_ENOMEM, "scl: workspace %zu B < required %zu B", workspace_bytes, need);
+    if (!d_workspace) return set_error(POLAR_ENOMEM, "scl: workspace %zu B < required %zu B", (size_t)0, need);
     if ((uintptr_t)d_workspace & 255) return set_error(POLAR_EALIGN, "scl: workspace must be 256-byte aligned");
+    if (workspace_bytes < need) {   // the kernels are persistent: run with as many CTAs as the workspace holds
+      const int64_t fit = (int64_t)(workspace_bytes / per_cta);
+      if (fit < 1) return set_error(POLAR_ENOMEM, "scl: workspace %zu B < required %zu B", workspace_bytes, per_cta);
+      pl.grid = fit;
+    }
   }
   SclParams P;
   P.logit = d_logit; P.fmask = d_frozen_mask; P.n = n; P.m = ilog2(n); P.B = B;

@@ -261,6 +261,35 @@ def test_scl_large_batch_vs_c_oracle(n, L, B, ebno):
     assert bad <= B // 100, "%d of %d lists differ" % (bad, B)
 
 
+def test_scl_misaligned_rows_fall_back_with_the_same_workspace():
+    """Rows that are not 16-byte aligned cannot use scl3's vector loads: the call falls back to scl2_kernel, which runs
+    with as many CTAs as the workspace polar_scl_workspace_bytes() reported (sized for scl3) holds.  Same bits."""
+    import torch
+    from oracle import polar_oracle as po
+    dk = _dk()
+    n, k, L, B = 1024, 512, 8, 2048
+    dev = torch.device("cuda", 0)
+    fp = po.rm_frozen_pos(n, n - k)
+    tables = dk.code_tables(fp, n, dev)
+    _, _, x = dk.awgn_frontend(tables, B, po.ebnodb2no(3.0, 2, k / n), 77)
+    want = dk.scl_decode(x, tables, L, want_packed=True, want_info=False, want_pm=True)
+    base = torch.empty(B * n + 1, dtype=torch.float32, device=dev)
+    xm = base[1:].view(B, n)
+    xm.copy_(x)
+    assert xm.data_ptr() % 16 == 4
+    need = int(dk.lib().polar_scl_workspace_bytes(n, L, B))
+    assert need < (1 << 29)                                   # scl3-sized (tens of MB), not scl2's default (> 1 GB)
+    ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+    wp = (ws.data_ptr() + 255) // 256 * 256
+    best = torch.empty((B, n // 32), dtype=torch.int32, device=dev)
+    pm = torch.empty((B, L), dtype=torch.float64, device=dev)
+    dk.check(dk.lib().polar_scl_decode(xm.data_ptr(), dk.ptr(tables.frozen_mask), n, L, B, dk.ptr(best), None, None, 0, dk.ptr(pm), None,
+                                       None, 0, wp, need, dk.stream_ptr(dev)))
+    torch.cuda.synchronize()
+    assert torch.equal(best, want["u_packed"])
+    assert torch.equal(pm.view(torch.int64), want["pm"].view(torch.int64))
+
+
 def test_scl3_literal_softplus_is_bit_identical_to_the_math_library():
     """polar_softplus.cuh: exp_nb / log_nb / softplus_literal return the same bits as CUDA's exp / log on [-30, 30]
     (incl. the clip values and fp32-representable arguments) -- the path-metric arithmetic of scl3 is the
