@@ -147,6 +147,39 @@ def test_sc3_extreme_frozen_patterns(n, mode, monkeypatch):
         assert np.array_equal(unpack_words(u_packed.cpu().numpy(), n), ref), len(fp)
 
 
+@pytest.mark.parametrize("n,B", [(1024, 1 << 18), (2048, 1 << 16)])
+def test_sc_stage_scratch_is_transparent(n, B, monkeypatch):
+    """polar_sc4.cu keeps the stage m-1 node of every codeword in flight in an L2-resident scratch indexed by the physical
+    SM.  A full-GPU batch (every SM, every warp slot, many batches per warp) must give the same bits with and without
+    it, also when two streams decode different batches at the same time (slots are per SM, never per launch)."""
+    import torch
+    from oracle import polar_oracle as po
+    dk = _dk()
+    k = n // 2
+    dev = torch.device("cuda", 0)
+    fp = po.rm_frozen_pos(n, n - k)
+    tables = dk.code_tables(fp, n, dev)
+    _, _, x = dk.awgn_frontend(tables, B, po.ebnodb2no(3.0, 2, k / n), 31337)
+    monkeypatch.setenv("POLAR_SC4_SCRATCH", "0")
+    _, ref = dk.sc_decode(x, tables, want_info=False, want_packed=True)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("POLAR_SC4_SCRATCH", "1")
+    _, got = dk.sc_decode(x, tables, want_info=False, want_packed=True)
+    assert torch.equal(got, ref)
+    # two streams, small launches that do not fill the GPU -> the two kernels really overlap
+    h = B // 64
+    outs = [torch.empty((h, n // 32), dtype=torch.int32, device=dev) for _ in range(8)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    torch.cuda.synchronize()
+    for i in range(8):
+        with torch.cuda.stream(streams[i % 2]):
+            dk.check(dk.lib().polar_sc_decode_f32(x[i * h:(i + 1) * h].data_ptr(), dk.ptr(tables.frozen_mask), n, h, dk.ptr(outs[i]),
+                                                  None, None, 0, streams[i % 2].cuda_stream))
+    torch.cuda.synchronize()
+    for i in range(8):
+        assert torch.equal(outs[i], ref[i * h:(i + 1) * h]), i
+
+
 def test_sc_extreme_frozen_patterns():
     """all-frozen, none-frozen, single info bit, alternating: exercises rate-0 / rate-1 shortcuts."""
     import torch
