@@ -75,7 +75,7 @@ int polar_sc_decode_boxplus_f32(const float *d_logit, const uint32_t *d_frozen_m
  * the argmin/gather of forward (:224-228) and, when crc_len > 0, the CRC-aided selection of
  * my_sn/fec/polar/dec.py:507-527 (+ my_sn/fec/crc.py:119-138).  fp64 LLR tree and path metrics,
  * pm += log(1+exp(-x)) evaluated literally; lazy copy-on-write of the tree through per-stage pointer tables.
- * Two mappings behind the one entry point: csrc/polar_scl3.cu (n in [256,4096], L in [2,32], 16-byte aligned rows:
+ * Two mappings behind the one entry point: csrc/polar_scl3.cu (n in [64,4096], L in [2,32], 16-byte aligned rows:
  * two virtual top stages computed from the channel row, tree in shared memory) and csrc/polar_scl.cu (everything
  * else); they return identical bits (tests/test_gpu_parity.py::test_scl3_equals_scl2_lists_and_path_metrics).
  *  L power of two, 1 <= L <= 32; n power of two, 2 <= n <= POLAR_SCL_MAX_N

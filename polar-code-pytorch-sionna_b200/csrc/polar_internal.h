@@ -24,7 +24,7 @@ int launch_sc3(const float *logit, const uint32_t *fmask, int n, int64_t B, uint
 int launch_sc4(const float *logit, const uint32_t *fmask, int n, int64_t B, uint32_t *u_packed, float *u_info,
                const int32_t *info_pos, int k, int warps, cudaStream_t st);
 
-// polar_scl3.cu: SCL decoder with compile-time tree, virtual top stages and on-chip LLR tree (n in [256, 4096], L in [2, 32])
+// polar_scl3.cu: SCL decoder with compile-time tree, virtual top stages and on-chip LLR tree (n in [64, 4096], L in [2, 32])
 struct Scl3Plan { int64_t grid; size_t ws_bytes_per_warp; };
 bool scl3_supported(int n, int L);
 int launch_scl3(const float *logit, const uint32_t *fmask, int n, int L, int64_t B, uint32_t *best, float *u_info,

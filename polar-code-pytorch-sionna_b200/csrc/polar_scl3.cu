@@ -1,4 +1,4 @@
-// polar_scl3.cu -- SCL decoder, third mapping (default for n >= 256, L >= 2): lane = (codeword, path) like
+// polar_scl3.cu -- SCL decoder, third mapping (default for n >= 64, L >= 2): lane = (codeword, path) like
 // scl2_kernel (polar_scl.cu), but with a compile-time tree and the LLR tree kept on chip.
 //
 // Same semantics as polar_scl.cu (x_run_sn_polar/polar/polar_scl.py:49-234, SURVEY.md Appendix A, L-survivor
@@ -76,7 +76,7 @@ PDEV auto op(T a, T b, unsigned u) {
 template <int L> struct Log2 { static constexpr int v = 1 + Log2<L / 2>::v; };
 template <> struct Log2<1> { static constexpr int v = 0; };
 
-// M = log2 n (8..12), L = list size (2..32), SS = number of LLR stages held in shared memory.
+// M = log2 n (6..12), L = list size (2..32), SS = number of LLR stages held in shared memory.
 template <int M, int L, int SS_>
 struct Cfg {
   static constexpr int N = 1 << M, NW = N / 32;
@@ -189,48 +189,96 @@ __global__ void __launch_bounds__(32 * WPC, CPS) scl3_kernel(const Params P) {
   auto vpass = [&](auto qc) {
     constexpr int Q = decltype(qc)::value;
     constexpr bool G9 = (Q & 4) != 0, G8 = (Q & 2) != 0, G7 = (Q & 1) != 0;
-    constexpr int WB = HT / 32;                                     // 32-element blocks per pass
-    const uint32_t *w9 = bl + ((1u << (M - 1 - 5)) - 1u) * 32 + gbase + (unsigned)((rowB >> (5 * (M - 1))) & 31u);
-    const uint32_t *w8 = bl + ((1u << (M - 2 - 5)) - 1u) * 32 + gbase + (unsigned)((rowB >> (5 * (M - 2))) & 31u);
-    const uint32_t *w7 = bl + ((1u << (M - 3 - 5)) - 1u) * 32 + gbase + (unsigned)((rowB >> (5 * (M - 3))) & 31u);
-    double *dst;
-    if constexpr (TOP < SS) dst = stage_sm(std::integral_constant<int, TOP>{}) + lane;
-    else dst = stage_gl(std::integral_constant<int, TOP>{}) + lane;
-#pragma unroll 1
-    for (int wb = 0; wb < WB; ++wb) {
-      uint32_t u9[4] = {0u, 0u, 0u, 0u}, u8[2] = {0u, 0u}, u7 = 0u;
-      if constexpr (G9) {
+    if constexpr (HT < 32) {
+      // n = 64 / 128: a pass is 8 / 16 elements; the partial sums of the three stages come from the word arrays
+      // (stage >= 5) or from the `small` register (stage < 5), four bits per float4 group
+      auto bits4 = [&](auto sc, int e0) -> uint32_t {
+        constexpr int S = decltype(sc)::value;
+        if constexpr (S >= 5) {
+          const uint32_t *w = bl + ((1u << (S - 5)) - 1u) * 32 + gbase + (unsigned)((rowB >> (5 * S)) & 31u);
+          return (w[(e0 >> 5) * 32] >> (e0 & 31)) & 0xFu;
+        } else {
+          return (small >> (((1u << S) - 1u) + (unsigned)e0)) & 0xFu;
+        }
+      };
+      double *dst = stage_sm(std::integral_constant<int, TOP>{}) + lane;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) u9[j] = w9[(wb + WB * j) * 32];
-      }
-      if constexpr (G8) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) u8[j] = w8[(wb + WB * j) * 32];
-      }
-      if constexpr (G7) u7 = w7[wb * 32];
-#pragma unroll 1
-      for (int e4 = 0; e4 < 8; ++e4) {
-        const int e = wb * 32 + e4 * 4;
+      for (int e = 0; e < HT; e += 4) {
         float4 c[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) c[j] = __ldg(reinterpret_cast<const float4 *>(ch + e + HT * j));
+        uint32_t u9[4] = {0u, 0u, 0u, 0u}, u8[2] = {0u, 0u}, u7 = 0u;
+        if constexpr (G9) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) u9[j] = bits4(std::integral_constant<int, M - 1>{}, e + HT * j);
+        }
+        if constexpr (G8) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) u8[j] = bits4(std::integral_constant<int, M - 2>{}, e + HT * j);
+        }
+        if constexpr (G7) u7 = bits4(std::integral_constant<int, M - 3>{}, e);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          const int bp = e4 * 4 + r;
           float x[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {   // LLR = -logit (polar_scl.py:219)
             const float v = (r == 0) ? c[j].x : (r == 1) ? c[j].y : (r == 2) ? c[j].z : c[j].w;
             x[j] = -v;
           }
-          const auto s90 = op<G9>(x[0], x[4], (u9[0] >> bp) & 1u);
-          const auto s91 = op<G9>(x[1], x[5], (u9[1] >> bp) & 1u);
-          const auto s92 = op<G9>(x[2], x[6], (u9[2] >> bp) & 1u);
-          const auto s93 = op<G9>(x[3], x[7], (u9[3] >> bp) & 1u);
-          const auto s80 = op<G8>(s90, s92, (u8[0] >> bp) & 1u);
-          const auto s81 = op<G8>(s91, s93, (u8[1] >> bp) & 1u);
-          const auto s7 = op<G7>(s80, s81, (u7 >> bp) & 1u);
+          const auto s90 = op<G9>(x[0], x[4], (u9[0] >> r) & 1u);
+          const auto s91 = op<G9>(x[1], x[5], (u9[1] >> r) & 1u);
+          const auto s92 = op<G9>(x[2], x[6], (u9[2] >> r) & 1u);
+          const auto s93 = op<G9>(x[3], x[7], (u9[3] >> r) & 1u);
+          const auto s80 = op<G8>(s90, s92, (u8[0] >> r) & 1u);
+          const auto s81 = op<G8>(s91, s93, (u8[1] >> r) & 1u);
+          const auto s7 = op<G7>(s80, s81, (u7 >> r) & 1u);
           dst[(e + r) * 32] = (double)s7;
+        }
+      }
+    } else {
+      constexpr int WB = HT / 32;                                     // 32-element blocks per pass
+      const uint32_t *w9 = bl + ((1u << (M - 1 - 5)) - 1u) * 32 + gbase + (unsigned)((rowB >> (5 * (M - 1))) & 31u);
+      const uint32_t *w8 = bl + ((1u << (M - 2 - 5)) - 1u) * 32 + gbase + (unsigned)((rowB >> (5 * (M - 2))) & 31u);
+      const uint32_t *w7 = bl + ((1u << (M - 3 - 5)) - 1u) * 32 + gbase + (unsigned)((rowB >> (5 * (M - 3))) & 31u);
+      double *dst;
+      if constexpr (TOP < SS) dst = stage_sm(std::integral_constant<int, TOP>{}) + lane;
+      else dst = stage_gl(std::integral_constant<int, TOP>{}) + lane;
+  #pragma unroll 1
+      for (int wb = 0; wb < WB; ++wb) {
+        uint32_t u9[4] = {0u, 0u, 0u, 0u}, u8[2] = {0u, 0u}, u7 = 0u;
+        if constexpr (G9) {
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) u9[j] = w9[(wb + WB * j) * 32];
+        }
+        if constexpr (G8) {
+  #pragma unroll
+          for (int j = 0; j < 2; ++j) u8[j] = w8[(wb + WB * j) * 32];
+        }
+        if constexpr (G7) u7 = w7[wb * 32];
+  #pragma unroll 1
+        for (int e4 = 0; e4 < 8; ++e4) {
+          const int e = wb * 32 + e4 * 4;
+          float4 c[8];
+  #pragma unroll
+          for (int j = 0; j < 8; ++j) c[j] = __ldg(reinterpret_cast<const float4 *>(ch + e + HT * j));
+  #pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int bp = e4 * 4 + r;
+            float x[8];
+  #pragma unroll
+            for (int j = 0; j < 8; ++j) {   // LLR = -logit (polar_scl.py:219)
+              const float v = (r == 0) ? c[j].x : (r == 1) ? c[j].y : (r == 2) ? c[j].z : c[j].w;
+              x[j] = -v;
+            }
+            const auto s90 = op<G9>(x[0], x[4], (u9[0] >> bp) & 1u);
+            const auto s91 = op<G9>(x[1], x[5], (u9[1] >> bp) & 1u);
+            const auto s92 = op<G9>(x[2], x[6], (u9[2] >> bp) & 1u);
+            const auto s93 = op<G9>(x[3], x[7], (u9[3] >> bp) & 1u);
+            const auto s80 = op<G8>(s90, s92, (u8[0] >> bp) & 1u);
+            const auto s81 = op<G8>(s91, s93, (u8[1] >> bp) & 1u);
+            const auto s7 = op<G7>(s80, s81, (u7 >> bp) & 1u);
+            dst[(e + r) * 32] = (double)s7;
+          }
         }
       }
     }
@@ -542,9 +590,9 @@ __global__ void math_selftest_kernel(uint64_t count, unsigned long long *mismatc
 bool scl3_supported(int n, int L) {
   const int m = ilog2(n);
 #if defined(POLAR_SCL3_DEV)
-  return m == 10 && L == 8;
+  return (m == 10 && L == 8) || ((m == 6 || m == 7) && L == 4);
 #else
-  return m >= 8 && m <= 12 && L >= 2 && L <= 32;
+  return m >= 6 && m <= 12 && L >= 2 && L <= 32;
 #endif
 }
 
@@ -592,7 +640,7 @@ int launch_scl3(const float *logit, const uint32_t *fmask, int n, int L, int64_t
   POLAR_SCL3_M(10)
 #else
 #define POLAR_SCL3_M(MM) if (m == MM) { POLAR_SCL3_L(MM, 2) POLAR_SCL3_L(MM, 4) POLAR_SCL3_L(MM, 8) POLAR_SCL3_L(MM, 16) POLAR_SCL3_L(MM, 32) }
-  POLAR_SCL3_M(8) POLAR_SCL3_M(9) POLAR_SCL3_M(10) POLAR_SCL3_M(11) POLAR_SCL3_M(12)
+  POLAR_SCL3_M(6) POLAR_SCL3_M(7) POLAR_SCL3_M(8) POLAR_SCL3_M(9) POLAR_SCL3_M(10) POLAR_SCL3_M(11) POLAR_SCL3_M(12)
 #endif
 #undef POLAR_SCL3_M
 #undef POLAR_SCL3_L

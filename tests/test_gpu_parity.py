@@ -338,7 +338,8 @@ def test_scl3_literal_softplus_is_bit_identical_to_the_math_library():
     assert cnt.tolist() == [0, 0, 0]
 
 
-@pytest.mark.parametrize("n,L,B,ebno", [(256, 4, 8192, 2.0), (512, 16, 2048, 3.0), (1024, 8, 8192, 3.0), (1024, 2, 4099, 4.0),
+@pytest.mark.parametrize("n,L,B,ebno", [(64, 8, 16384, 1.0), (64, 32, 1025, 2.0), (128, 4, 16384, 2.0), (128, 16, 4100, 2.0),
+                                        (256, 4, 8192, 2.0), (512, 16, 2048, 3.0), (1024, 8, 8192, 3.0), (1024, 2, 4099, 4.0),
                                         (2048, 32, 515, 3.5), (4096, 8, 1024, 4.0)])
 def test_scl3_equals_scl2_lists_and_path_metrics(n, L, B, ebno, monkeypatch):
     """The two SCL mappings (polar_scl3.cu: virtual top stages, pair loop; polar_scl.cu scl2_kernel: everything
