@@ -31,6 +31,9 @@ namespace polar {
 #ifndef POLAR_SCL3_RANK
 #define POLAR_SCL3_RANK 1
 #endif
+#ifndef POLAR_SCL3_VUNROLL
+#define POLAR_SCL3_VUNROLL 1
+#endif
 #ifndef POLAR_SCL3_DISCARD
 #define POLAR_SCL3_DISCARD 1
 #endif
@@ -40,6 +43,7 @@ namespace polar {
 
 namespace scl3 {
 
+constexpr int kVUnroll = POLAR_SCL3_VUNROLL;   // channel-load groups in flight in the virtual passes
 constexpr double kLlrMaxD = 30.0;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(32 * WPC, CPS) scl3_kernel(const Params P) {
           for (int j = 0; j < 2; ++j) u8[j] = w8[(wb + WB * j) * 32];
         }
         if constexpr (G7) u7 = w7[wb * 32];
-  #pragma unroll 1
+  #pragma unroll kVUnroll
         for (int e4 = 0; e4 < 8; ++e4) {
           const int e = wb * 32 + e4 * 4;
           float4 c[8];
