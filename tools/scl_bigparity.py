@@ -32,5 +32,13 @@ list_bad = 0
 for b in range(B):
     list_bad += set(map(bytes, got[b])) != set(map(bytes, u_ref[b]))
 pm_exact = int((pm.view(np.int64) == pm_ref.view(np.int64)).all(axis=1).sum())
+bad_idx = np.nonzero((got[:, 0] != u_ref[:, 0]).any(axis=1))[0]
+if len(bad_idx):
+    # which side does the numpy restatement (the reference's own exp / log) take on those codewords?
+    sub = x[torch.from_numpy(bad_idx[:8]).to(dev)].cpu().numpy()
+    u_np, pm_np = po.scl_decode_full(sub, po.frozen_vec(fp, n), L)
+    for j, bidx in enumerate(bad_idx[:8]):
+        print("  codeword %d: numpy restatement agrees with the GPU: %s, with the C restatement: %s; best metrics GPU %.12g C %.12g numpy %.12g" %
+              (bidx, np.array_equal(u_np[j, 0], got[bidx, 0]), np.array_equal(u_np[j, 0], u_ref[bidx, 0]), pm[bidx, 0], pm_ref[bidx, 0], pm_np[j, 0]))
 print("n=%d L=%d B=%d Eb/N0=%.1f dB: best path differs on %d codewords, list (as a set) on %d, all L path metrics bit-identical on %d, "
       "max rel err of the best metric %.2e  (oracle %.1f s)" % (n, L, B, ebno, best_bad, list_bad, pm_exact, rel0.max(), t1 - t0))
