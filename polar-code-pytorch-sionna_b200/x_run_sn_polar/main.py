@@ -49,11 +49,14 @@ def parse_config(argv=None):
   except ImportError:
     import argparse
     ap = argparse.ArgumentParser()
+    import typing
     d = PolarConfig()
+    hints = typing.get_type_hints(PolarConfig)                     # the annotation decides (snr_end: float = 5)
     for f, v in vars(d).items():
-      if isinstance(v, bool): ap.add_argument("--" + f, type=lambda s: s.lower() in ("1", "true", "yes"), default=v)
+      t = hints.get(f, type(v))
+      if t is bool: ap.add_argument("--" + f, type=lambda s: s.lower() in ("1", "true", "yes"), default=v)
       elif isinstance(v, list): ap.add_argument("--" + f, type=lambda s: [t for t in s.strip("[]").split(",") if t], default=v)
-      else: ap.add_argument("--" + f, type=type(v), default=v)
+      else: ap.add_argument("--" + f, type=t if t in (int, float, str) else type(v), default=v)
     return PolarConfig(**vars(ap.parse_args(argv)))
 
 

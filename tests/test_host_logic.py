@@ -216,3 +216,31 @@ def test_5g_rate_matching_plans_match_reference():
         Polar5GEncoder(100, 50)
     with pytest.raises(AssertionError):
         Polar5GEncoder(200, 400, channel_type="downlink")
+
+
+def test_main_cli_fallback_parser_follows_the_annotations():
+    """x_run_sn_polar/main.py without pyrallis: option types come from the dataclass annotations of config.py:5-26
+    (`snr_end: float = 5` must accept 4.5, `algos` the reference's bracket list, `verbose` a boolean word)."""
+    import importlib.util
+    import sys
+    for p in (PKG, os.path.join(PKG, "x_run_sn_polar")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    saved = sys.modules.get("pyrallis")
+    sys.modules["pyrallis"] = None                      # force the argparse fallback
+    try:
+        spec = importlib.util.spec_from_file_location("polar_main_cli", os.path.join(PKG, "x_run_sn_polar", "main.py"))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        c = m.parse_config(["--k", "1024", "--n", "2048", "--algos", "[sc,scl]", "--list_size", "32", "--snr_end", "4.5",
+                            "--bs", "65536", "--mc_iter", "16", "--verbose", "true"])
+    finally:
+        if saved is None:
+            sys.modules.pop("pyrallis", None)
+        else:
+            sys.modules["pyrallis"] = saved
+    assert (c.k, c.n, c.list_size, c.bs, c.mc_iter) == (1024, 2048, 32, 65536, 16)
+    assert c.snr_end == 4.5 and isinstance(c.snr_end, float)
+    assert c.algos == ["sc", "scl"] and c.verbose is True
+    d = m.parse_config([])
+    assert (d.k, d.n, d.bs, d.snr_end, d.seed) == (32, 64, 3, 5, 42)
