@@ -171,21 +171,27 @@ def _g64(a, b, u):
     return np.multiply((1 - 2 * u), a) + b
 
 
-def _softplus_neg(x, use_log1p=False):
-    """polar_scl.py:82-83: log(1 + exp(-x)), literal (NOT log1p, NOT max(0,-x))."""
-    if use_log1p:
-        return np.log1p(np.exp(-x))
-    return np.log(1 + np.exp(-x))
+def _softplus_neg(x, use_log1p=False, jitter=None):
+    """polar_scl.py:82-83: log(1 + exp(-x)), literal (NOT log1p, NOT max(0,-x)).
+    `jitter` (a numpy Generator) moves every result by -1 / 0 / +1 ulp at random: the spread of exp/log
+    implementations (numpy SIMD, glibc, CUDA) in the last bit, used to detect codewords whose ranking the
+    reference itself does not reproduce across math libraries."""
+    v = np.log1p(np.exp(-x)) if use_log1p else np.log(1 + np.exp(-x))
+    if jitter is not None:
+        d = jitter.integers(-1, 2, size=np.shape(v))
+        v = np.where(d > 0, np.nextafter(v, np.inf), np.where(d < 0, np.nextafter(v, -np.inf), v))
+    return v
 
 
-def scl_decode_full(logits, frozen, list_size, use_log1p=False, stable_sort=True):
+def scl_decode_full(logits, frozen, list_size, use_log1p=False, stable_sort=True, ulp_jitter_seed=None):
     """Equivalent L-survivor formulation of polar_scl.py:121-209 (bit-exact incl. PMs):
     L paths with pm = [0, 30, ..., 30] (polar_scl.py:192-194; the reference's 2L slots are these L
     paths duplicated pairwise); frozen leaf: pm += softplus(-llr) (u=0); info leaf: fork every path
     (u=0: pm+softplus(-llr), u=1: pm+softplus(+llr)), sort the 2L candidates ascending, keep L.
     Returns (u_hat uint8 [B, L, n] sorted by pm ascending, pm float64 [B, L]).
-    `use_log1p` / `stable_sort` give the oracle *variants* used to detect ill-conditioned lists
-    (SURVEY 8c)."""
+    `use_log1p` / `stable_sort` / `ulp_jitter_seed` give the oracle *variants* used to detect ill-conditioned
+    lists."""
+    jit = None if ulp_jitter_seed is None else np.random.default_rng(ulp_jitter_seed)
     llr_ch = (np.float32(-1.0) * np.asarray(logits, dtype=np.float32)).astype(np.float64)
     B, n = llr_ch.shape
     L = int(list_size)
@@ -213,10 +219,10 @@ def scl_decode_full(logits, frozen, list_size, use_log1p=False, stable_sort=True
         if ln == 1:
             x = np.maximum(np.minimum(frame["L"][:, :, 0], LLR_MAX), -LLR_MAX)   # polar_scl.py:81
             if frozen[a]:
-                state["pm"] = state["pm"] + _softplus_neg(x, use_log1p)        # u=0, polar_scl.py:82
+                state["pm"] = state["pm"] + _softplus_neg(x, use_log1p, jit)   # u=0, polar_scl.py:82
                 return np.zeros((B, L, 1), dtype=np.uint8)
-            c0 = state["pm"] + _softplus_neg(x, use_log1p)                      # u_hat = 0
-            c1 = state["pm"] + _softplus_neg(-x, use_log1p)                     # u_hat = 1
+            c0 = state["pm"] + _softplus_neg(x, use_log1p, jit)                 # u_hat = 0
+            c1 = state["pm"] + _softplus_neg(-x, use_log1p, jit)                # u_hat = 1
             # reference slot order before the sort: [L paths with u=0 | L paths with u=1]
             cand = np.concatenate([c0, c1], axis=1)
             order = np.argsort(cand, axis=1, kind=kind)[:, :L]                  # polar_scl.py:86-92
@@ -250,6 +256,33 @@ def scl_decode_full(logits, frozen, list_size, use_log1p=False, stable_sort=True
     pm = np.take_along_axis(state["pm"], order, axis=1)
     u = state["u"][bar, order]
     return u, pm
+
+
+def path_metric(logits, frozen, u):
+    """Path metric the reference accumulates along a GIVEN decision vector u [B, n] (polar_scl.py:69-85 applied
+    to one path whose leaf decisions are forced): sum over all leaves of log(1 + exp(-(1-2u).clip(llr))), with the
+    fp64 f / g tree of polar_scl.py:93-108.  Checker for "is this a legitimate path and is its metric right"."""
+    llr = (np.float32(-1.0) * np.asarray(logits, dtype=np.float32)).astype(np.float64)
+    u = np.asarray(u, dtype=np.uint8)
+    B, n = llr.shape
+    pm = np.zeros(B)
+
+    def rec(a, Lc):
+        nonlocal pm
+        ln = Lc.shape[1]
+        if ln == 1:
+            x = np.maximum(np.minimum(Lc[:, 0], LLR_MAX), -LLR_MAX)
+            bit = u[:, a].astype(np.float64)
+            assert not (frozen[a] and u[:, a].any()), "frozen position decided 1"
+            pm = pm + np.log(1 + np.exp(-(1 - 2 * bit) * x))
+            return u[:, a:a + 1]
+        h = ln // 2
+        bl = rec(a, _f64(Lc[:, :h], Lc[:, h:]))
+        br = rec(a + h, _g64(Lc[:, :h], Lc[:, h:], bl.astype(np.float64)))
+        return np.concatenate([bl ^ br, br], axis=1)
+
+    rec(0, llr)
+    return pm
 
 
 def scl_decode(logits, frozen_pos, n, list_size):

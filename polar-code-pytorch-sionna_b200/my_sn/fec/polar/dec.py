@@ -32,8 +32,8 @@ class SC_Dec(nn.Module):
     self._use_fast_sc = False
     self.device = device
 
-  def decode_packed(self, logits, tables):
-    return dk.sc_decode(logits, tables, want_info=False, want_packed=True, boxplus=True)[1]
+  def decode_packed(self, logits, tables, out=None):
+    return dk.sc_decode(logits, tables, want_info=False, want_packed=True, boxplus=True, out_packed=out)[1]
 
   def forward(self, inputs):
     assert inputs.shape[-1] == self.n, "Last input dim must be of len n."
@@ -116,11 +116,11 @@ class SCL_Dec(nn.Module):
       rows = self._crc_rows[str(dev)] = tc.from_numpy(self._crc_rows_np.view(np.int32).copy()).to(dev)
     return rows, self._k_crc
 
-  def decode_packed(self, logits, tables):
+  def decode_packed(self, logits, tables, out=None):
     """Device fast path of the on-device Monte-Carlo loop: bit-packed decisions of the (CRC-)selected path."""
     rows, ln = self._rows_on(tables.dev)
     return dk.scl_decode(logits, tables, self._list_size, crc_rows=rows, crc_len=ln, want_info=False,
-                         want_packed=True, boxplus=self._boxplus)["u_packed"]
+                         want_packed=True, boxplus=self._boxplus, out_packed=out)["u_packed"]
 
   def forward(self, inputs):
     assert inputs.dtype == self.output_dtype, "Invalid input dtype."

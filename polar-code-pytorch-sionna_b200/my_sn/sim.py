@@ -46,24 +46,74 @@ def _dist():
 
 
 def _device_loop_ok(mc_fun, soft_estimates, count_fn):
-  """The on-device loop applies to the fused AWGN link model with a decoder that has the packed fast path."""
+  """The on-device loop applies to link models that provide the `device_frontend` hook (fused AWGN / BEC front end)
+  together with a decoder that has the packed fast path."""
   return (count_fn is None and not soft_estimates and getattr(mc_fun, "fused", False)
+          and callable(getattr(mc_fun, "device_frontend", None))
           and not getattr(mc_fun, "cw_estimates", True) and hasattr(getattr(mc_fun, "decoder", None), "decode_packed")
           and tc.cuda.is_available())
 
 
+class StopPredictor:
+  """Should iteration ii+1 of an SNR point be queued before the stop flag of iteration ii has come back?
+
+  The device loop never lets the GPU wait for the host inside a point: it queues one iteration ahead.  The price is one
+  discarded iteration per point (the one queued past the stop) -- 50 % of the work of a sweep whose points stop after a
+  single iteration (BASELINE configs[3]: 65536 block errors against a target of 1000).  So the look-ahead is skipped when
+  the counters seen so far say, with margin, that the iterations already queued will reach a target: rate per iteration
+  from this point's known iterations, else a tenth of the previous point's (error rates fall with Eb/N0).  Either
+  misprediction only costs time -- a discarded iteration or one host round trip -- never a different result."""
+
+  def __init__(self, target_bit_errs, target_block_errs, max_mc_iter, damp=0.1):
+    self.targets = (target_bit_errs, target_block_errs)
+    self.max_iter = int(max_mc_iter)
+    self.damp = damp
+    self.prev_rate = None            # (bit errors, block errors) per iteration of the previous point
+    self.start_point()
+
+  def start_point(self):
+    self.known_iters, self.known = 0, (0, 0)
+
+  def observe(self, iters, bit_errs, block_errs):
+    self.known_iters, self.known = int(iters), (int(bit_errs), int(block_errs))
+
+  def end_point(self):
+    if self.known_iters:
+      self.prev_rate = tuple(c / self.known_iters for c in self.known)
+
+  def speculate(self, queued):
+    """queued: iterations of this point already queued (results of the last queued - known_iters unknown)."""
+    if queued >= self.max_iter:
+      return False
+    if self.known_iters:
+      rate = tuple(c / self.known_iters for c in self.known)
+    elif self.prev_rate is not None:
+      rate = tuple(c * self.damp for c in self.prev_rate)
+    else:
+      return True
+    for tgt, cum, r in zip(self.targets, self.known, rate):
+      if tgt is None:
+        continue
+      pred = cum + r * (queued - self.known_iters)
+      if pred >= tgt + 3.0 * pred ** 0.5 + 1.0:
+        return False                 # the queued iterations will (almost surely) reach the target: wait for the flag
+    return True
+
+
 def sim_ber_device(model, ebno_dbs, batch_size, max_mc_iter, target_bit_errs=None, target_block_errs=None,
-                   early_stop=True, verbose=True, return_counters=False):
+                   early_stop=True, verbose=True, return_counters=False, lookahead=True, stats=None):
   """the Monte-Carlo loop of sim.py:79-133 with every per-iteration step on the device.
 
-  One iteration = front-end kernel (bits -> encoder -> QPSK -> AWGN -> logits) -> decoder kernel (bit-packed
-  decisions) -> packed error counter -> [sharded: one 4 x int64 NCCL all-reduce] -> `polar_mc_control`, a one-thread
-  kernel that accumulates the counters and evaluates the stop rules (target bit errors, target block errors, max
-  iterations).  The host never reads a counter inside an SNR point: it keeps ONE iteration queued ahead and only
-  polls the stop flag of the iteration before that from pinned memory, so the GPU is never idle; the iteration that
-  was queued past the stop is ignored by the control kernel (and its random numbers are handed to the next point),
-  which makes the result identical to the host loop (`sim_ber(..., on_device=False)`) for the same seed.
-  Returns (ber, bler) like sim_ber; with return_counters also the int64 [P,4] counters, status and iterations."""
+  One iteration = front-end kernel (bits -> encoder -> QPSK -> AWGN -> logits; `model.device_frontend`) -> decoder kernel
+  (bit-packed decisions) -> packed error counter -> [sharded: one 4 x int64 NCCL all-reduce] -> `polar_mc_control`, a
+  one-thread kernel that accumulates the counters and evaluates the stop rules (target bit errors, target block errors,
+  max iterations).  All buffers are allocated once per call.  The host never reads a counter synchronously inside an SNR
+  point: it keeps ONE iteration queued ahead (unless `StopPredictor` says the queued work will reach a target) and polls
+  the stop flag of the iteration before from pinned memory; an iteration queued past the stop is ignored by the control
+  kernel and its random numbers are handed to the next point, which makes the result identical to the host loop
+  (`sim_ber(..., on_device=False)`) for the same seed.
+  Returns (ber, bler) like sim_ber; with return_counters also the int64 [P,4] counters, status and iterations.
+  `stats` (dict, optional) receives {"queued": iterations launched, "counted": iterations counted}."""
   dist = _dist()
   rank0 = dist is None or dist.get_rank() == 0
   verbose = verbose and rank0
@@ -75,44 +125,66 @@ def sim_ber_device(model, ebno_dbs, batch_size, max_mc_iter, target_bit_errs=Non
   tables = dk.code_tables(frozen_pos, model.n, dev)
   if model._seed is None:
     model._seed = int(tc.randint(0, 2 ** 62, (1,)).item())
-  from my_sn.trans import ebno as _ebno
   ebno_dbs = np.asarray(ebno_dbs, dtype=np.float32)
   P = ebno_dbs.shape[0]
   B = int(batch_size)
+  max_mc_iter = int(max_mc_iter)
   counters = np.zeros((P, 4), dtype=np.int64)
   status = np.zeros(P, dtype=np.int64)
   iters = np.zeros(P, dtype=np.int64)
   runtime = np.zeros(P)
+  n_queued = 0
   status_levels = ["not simulated", "reached max iter       ", "no errors - early stop",
                    "reached target bit errors", "reached target block errors"]
   fmt = "{: >9} |{: >11} |{: >11} |{: >12} |{: >12} |{: >13} |{: >12} |{: >12} |{: >10}"
+  DEPTH = 2 if lookahead else 1
+  pred = StopPredictor(target_bit_errs, target_block_errs, max_mc_iter)
   with tc.cuda.device(dev):
+    nw = dk.words(model.n)
+    u_tx = tc.empty((B, nw), dtype=tc.int32, device=dev)
+    llr = tc.empty((B, model.n), dtype=tc.float32, device=dev)
+    u_hat = tc.empty((B, nw), dtype=tc.int32, device=dev)
     state = tc.zeros(8, dtype=tc.int64, device=dev)
     delta = tc.zeros(4, dtype=tc.int64, device=dev)
     sizes = tc.tensor([0, 0, B * tables.k, B], dtype=tc.int64, device=dev)
-    host = [tc.zeros(8, dtype=tc.int64).pin_memory() for _ in range(2)]
-    events = [tc.cuda.Event() for _ in range(2)]
+    host = [tc.zeros(8, dtype=tc.int64).pin_memory() for _ in range(DEPTH)]
+    events = [tc.cuda.Event() for _ in range(DEPTH)]
+
+    def queue(i, ii, offset0):
+      model.device_frontend(tables, B, ebno_dbs[i], model._seed, offset0 + ii * B, (u_tx, llr))
+      dec.decode_packed(llr, tables, out=u_hat)
+      delta.copy_(sizes)                                     # (0, 0, bits, blocks) of this rank's shard
+      dk.count_errors_packed(u_tx, u_hat, tables.info_mask, model.n, delta)
+      if dist is not None:
+        dist.all_reduce(delta)                               # stream-ordered NCCL all-reduce of 4 x int64
+      dk.mc_control(delta, state, target_bit_errs, target_block_errs, max_mc_iter)
+      host[ii % DEPTH].copy_(state, non_blocking=True)
+      events[ii % DEPTH].record()
+
     for i in range(P):
       t0 = time.perf_counter()
-      no = _ebno.ebnodb2no(float(ebno_dbs[i]), model.n_bits_per_sym, model.coderate)
       state.zero_()
       offset0 = model._offset
-      for ii in range(max_mc_iter):
-        u_tx, _, llr = dk.awgn_frontend(tables, B, no, model._seed, offset0 + ii * B)
-        u_hat = dec.decode_packed(llr, tables)
-        delta.copy_(sizes)                                     # (0, 0, bits, blocks) of this rank's shard
-        dk.count_errors_packed(u_tx, u_hat, tables.info_mask, model.n, delta)
-        if dist is not None:
-          dist.all_reduce(delta)                               # stream-ordered NCCL all-reduce of 4 x int64
-        dk.mc_control(delta, state, target_bit_errs, target_block_errs, max_mc_iter)
-        host[ii & 1].copy_(state, non_blocking=True)
-        events[ii & 1].record()
-        if ii >= 1:                                            # poll the iteration BEFORE the one just queued
-          events[(ii - 1) & 1].synchronize()
-          if int(host[(ii - 1) & 1][4]):
-            break
+      pred.start_point()
+      queued = known = 0
+      while True:
+        if queued < max_mc_iter and queued - known < DEPTH and (queued == known or pred.speculate(queued)):
+          queue(i, queued, offset0)
+          queued += 1
+          continue
+        if known == queued:
+          break
+        events[known % DEPTH].synchronize()                  # oldest iteration whose outcome is still unknown
+        h = host[known % DEPTH]
+        known += 1
+        pred.observe(int(h[6]), int(h[0]), int(h[1]))
+        if int(h[4]):
+          break
+      n_queued += queued
       tc.cuda.current_stream(dev).synchronize()
       st = state.cpu().numpy()
+      pred.observe(int(st[6]), int(st[0]), int(st[1]))
+      pred.end_point()
       counters[i] = st[:4]; status[i] = st[5]; iters[i] = st[6]
       model._offset = offset0 + int(st[6]) * B                 # random numbers of a discarded iteration are reused
       runtime[i] = time.perf_counter() - t0
@@ -130,6 +202,8 @@ def sim_ber_device(model, ebno_dbs, batch_size, max_mc_iter, target_bit_errs=Non
         if verbose:
           print(f"\nSimu stopped as no error occurred @ EbNo = {ebno_dbs[i]:.1f} dB.\n")
         break
+  if stats is not None:
+    stats.update(queued=int(n_queued), counted=int(iters.sum()), blocks=int(counters[:, 3].sum()))
   with np.errstate(divide='ignore', invalid='ignore'):
     ber = np.nan_to_num(counters[:, 0] / counters[:, 2])
     bler = np.nan_to_num(counters[:, 1] / counters[:, 3])

@@ -13,7 +13,7 @@ import os
 import numpy as np
 import torch as tc
 
-from config import device
+from config import device  # noqa: F401  (re-exported: main.py star-imports this module)
 
 # ---- polarization kernels (reference d_kernels.py:3-11) -----------------------------------------
 
@@ -26,7 +26,9 @@ def gen_arikan(F2, lay):
   return FN
 
 
-F2 = tc.tensor([[1, 0], [1, 1]], dtype=tc.float32, device=device)
+# Host tensors: frozen-set construction (froze.py) is host-side, and creating them on `device` at import time would open a
+# CUDA context on GPU 0 in every torchrun rank before main.py selects LOCAL_RANK.
+F2 = tc.tensor([[1, 0], [1, 1]], dtype=tc.float32, device='cpu')
 F4 = gen_arikan(F2, 2); F8 = gen_arikan(F2, 3)
 F16 = gen_arikan(F2, 4); F32 = gen_arikan(F2, 5)
 
@@ -184,14 +186,16 @@ def _prep_logits(x, n, dev):
   return x
 
 
-def sc_decode(logits, tables, want_info=True, want_packed=False, boxplus=False):
+def sc_decode(logits, tables, want_info=True, want_packed=False, boxplus=False, out_packed=None):
   """polar_sc_decode_f32 (min-sum f) or polar_sc_decode_boxplus_f32 (exact boxplus f, my_sn SC_Dec).
-  logits [B,n] (any float dtype/device) -> (u_info fp32 [B,k] | None, u_packed int32 | None)."""
+  logits [B,n] (any float dtype/device) -> (u_info fp32 [B,k] | None, u_packed int32 | None).
+  out_packed: caller-owned int32 [B, words(n)] buffer for the packed decisions (Monte-Carlo loop: no allocation per call)."""
   dev = tables.dev
   x = _prep_logits(logits, tables.n, dev)
   B = x.shape[0]
   u_info = tc.empty((B, tables.k), dtype=tc.float32, device=dev) if want_info else None
-  u_packed = tc.empty((B, words(tables.n)), dtype=tc.int32, device=dev) if want_packed else None
+  u_packed = out_packed if out_packed is not None else (
+    tc.empty((B, words(tables.n)), dtype=tc.int32, device=dev) if want_packed else None)
   with tc.cuda.device(dev):
     fn = lib().polar_sc_decode_boxplus_f32 if boxplus else lib().polar_sc_decode_f32
     check(fn(ptr(x), ptr(tables.frozen_mask), tables.n, B, ptr(u_packed), ptr(u_info), ptr(tables.info_pos), tables.k,
@@ -203,7 +207,7 @@ _WS_CACHE = {}
 
 
 def scl_decode(logits, tables, list_size, crc_rows=None, crc_len=0, want_info=True, want_packed=False,
-               want_pm=False, want_list=False, boxplus=False):
+               want_pm=False, want_list=False, boxplus=False, out_packed=None):
   """polar_scl_decode (min-sum f) or polar_scl_decode_boxplus (exact boxplus f, my_sn SCL_Dec)
   -> dict(u_info, u_packed, pm [B,L] fp64, list [B,L,words] int32)."""
   dev = tables.dev
@@ -212,7 +216,9 @@ def scl_decode(logits, tables, list_size, crc_rows=None, crc_len=0, want_info=Tr
   out = {"u_info": None, "u_packed": None, "pm": None, "list": None}
   if want_info:
     out["u_info"] = tc.empty((B, tables.k), dtype=tc.float32, device=dev)
-  if want_packed:
+  if out_packed is not None:
+    out["u_packed"] = out_packed
+  elif want_packed:
     out["u_packed"] = tc.empty((B, words(n)), dtype=tc.int32, device=dev)
   if want_pm:
     out["pm"] = tc.empty((B, L), dtype=tc.float64, device=dev)
@@ -254,26 +260,27 @@ def encode_packed(u_full_packed, n):
   return out
 
 
-def awgn_frontend(tables, batch_size, no, seed, offset=0, want_codeword=False):
-  """polar_awgn_frontend -> (u_packed int32 [B,words], c_packed | None, logits fp32 [B,n])."""
+def awgn_frontend(tables, batch_size, no, seed, offset=0, want_codeword=False, out=None):
+  """polar_awgn_frontend -> (u_packed int32 [B,words], c_packed | None, logits fp32 [B,n]).
+  out = (u_packed, logits): caller-owned buffers (Monte-Carlo loop: no allocation per call)."""
   dev = tables.dev
   B, n = int(batch_size), tables.n
-  u = tc.empty((B, words(n)), dtype=tc.int32, device=dev)
+  u = out[0] if out is not None else tc.empty((B, words(n)), dtype=tc.int32, device=dev)
   c = tc.empty((B, words(n)), dtype=tc.int32, device=dev) if want_codeword else None
-  logit = tc.empty((B, n), dtype=tc.float32, device=dev)
+  logit = out[1] if out is not None else tc.empty((B, n), dtype=tc.float32, device=dev)
   with tc.cuda.device(dev):
     check(lib().polar_awgn_frontend(int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset), float(no), ptr(tables.frozen_mask), n, B,
                                     ptr(u), ptr(c), ptr(logit), stream_ptr(dev)))
   return u, c, logit
 
 
-def bec_frontend(tables, batch_size, pe, seed, offset=0, llr_max=100.0, want_codeword=False):
+def bec_frontend(tables, batch_size, pe, seed, offset=0, llr_max=100.0, want_codeword=False, out=None):
   """polar_bec_frontend -> (u_packed int32 [B,words], c_packed | None, logits fp32 [B,n] in {0, +-llr_max})."""
   dev = tables.dev
   B, n = int(batch_size), tables.n
-  u = tc.empty((B, words(n)), dtype=tc.int32, device=dev)
+  u = out[0] if out is not None else tc.empty((B, words(n)), dtype=tc.int32, device=dev)
   c = tc.empty((B, words(n)), dtype=tc.int32, device=dev) if want_codeword else None
-  logit = tc.empty((B, n), dtype=tc.float32, device=dev)
+  logit = out[1] if out is not None else tc.empty((B, n), dtype=tc.float32, device=dev)
   with tc.cuda.device(dev):
     check(lib().polar_bec_frontend(int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset), float(pe), float(llr_max),
                                    ptr(tables.frozen_mask), n, B, ptr(u), ptr(c), ptr(logit), stream_ptr(dev)))

@@ -31,10 +31,10 @@ class SC_Dec(nn.Module):
     self.device = device
     self.complexity = None
 
-  def decode_packed(self, logits, tables):
+  def decode_packed(self, logits, tables, out=None):
     """Device fast path of the on-device Monte-Carlo loop: logits [B,n] on the GPU -> bit-packed decisions
     int32 [B, n/32] (all n positions, frozen = 0), no fp32 [B,k] tensor is materialised."""
-    return dk.sc_decode(logits, tables, want_info=False, want_packed=True)[1]
+    return dk.sc_decode(logits, tables, want_info=False, want_packed=True, out_packed=out)[1]
 
   def forward(self, inputs):
     self.complexity = 0

@@ -47,9 +47,9 @@ class SCL_Dec(nn.Module):
   @property
   def llr_max(self): return self._llr_max
 
-  def decode_packed(self, logits, tables):
+  def decode_packed(self, logits, tables, out=None):
     """Device fast path of the on-device Monte-Carlo loop: bit-packed decisions of the best path."""
-    return dk.scl_decode(logits, tables, self._list_size, want_info=False, want_packed=True)["u_packed"]
+    return dk.scl_decode(logits, tables, self._list_size, want_info=False, want_packed=True, out_packed=out)["u_packed"]
 
   def forward(self, inputs):
     assert inputs.dtype == self.output_dtype, "Invalid input dtype."

@@ -36,6 +36,12 @@ class System_AWGN_model(nn.Module):
     self.awgn_channel = awgn.AWGN(device=dev)
     self._layers = dev
 
+  def device_frontend(self, tables, batch_size, ebno_db, seed, offset, out):
+    """Hook of the on-device Monte-Carlo loop (my_sn/sim.py::sim_ber_device): one launch of polar_awgn_frontend into the
+    caller-owned buffers out = (u_packed, logits).  A link model without this method runs the host loop."""
+    no = ebno.ebnodb2no(float(ebno_db), self.n_bits_per_sym, self.coderate)
+    dk.awgn_frontend(tables, batch_size, no, seed, offset, out=out)
+
   def forward(self, batch_size, ebno_db):
     dev = dk.cuda_device(self.device)
     no = ebno.ebnodb2no(float(ebno_db), self.n_bits_per_sym, self.coderate)

@@ -25,6 +25,12 @@ class System_BEC_model(nn.Module):
     self._seed = seed
     self._offset = 0
 
+  def device_frontend(self, tables, batch_size, ebno_db, seed, offset, out):
+    """Hook of the on-device Monte-Carlo loop (my_sn/sim.py::sim_ber_device): one launch of polar_bec_frontend into the
+    caller-owned buffers out = (u_packed, logits); `ebno_db` is the erasure probability (bec_model.py:16-17)."""
+    pe = float(min(max(float(ebno_db), 0.), 1.))
+    dk.bec_frontend(tables, batch_size, pe, seed, offset, llr_max=float(self.channel.llr_max), out=out)
+
   def forward(self, batch_size, ebno_db):
     dev = dk.cuda_device(self.device)
     pe = float(min(max(float(ebno_db), 0.), 1.))

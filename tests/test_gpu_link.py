@@ -299,6 +299,39 @@ def test_on_device_monte_carlo_loop_equals_host_loop(dec_kind):
     assert torch.equal(r1[0], r2[0]) and torch.equal(r1[1], r2[1])
 
 
+def test_device_loop_lookahead_and_bec_model():
+    """(a) A sweep whose points stop after one iteration (configs[3] regime) wastes at most one look-ahead iteration in
+    total (StopPredictor), with results identical to the loop without look-ahead.  (b) ADVICE r01: System_BEC_model goes
+    through sim_ber on both paths (its own `device_frontend` hook: erasures, not AWGN) with identical counters."""
+    torch, dk, po, co, dev = _env()
+    from polar.enc import PolarEncoder
+    from polar.polar_sc import SC_Dec
+    from z_sys_model.awgn_model import System_AWGN_model
+    from z_sys_model.bec_model import System_BEC_model
+    from my_sn.sim import sim_ber, sim_ber_device
+    n, k, bs = 256, 128, 4096
+    fp = po.rm_frozen_pos(n, n - k)
+    ebnos = np.array([0.0, 0.5, 1.0, 1.5, 2.0], dtype=np.float32)           # BLER >> 100 / 4096 everywhere
+    mk = lambda: System_AWGN_model(n, k, PolarEncoder(fp, n, None), SC_Dec(fp, n), seed=17)
+    st_a, st_b = {}, {}
+    a = sim_ber_device(mk(), ebnos, bs, 16, target_block_errs=100, verbose=False, return_counters=True, stats=st_a)
+    b = sim_ber_device(mk(), ebnos, bs, 16, target_block_errs=100, verbose=False, return_counters=True, stats=st_b, lookahead=False)
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+    assert st_b["queued"] == st_b["counted"] == len(ebnos)
+    assert st_a["counted"] == len(ebnos) and st_a["queued"] <= len(ebnos) + 1, st_a
+    # long points: look-ahead stays on (one discarded iteration per point at most)
+    st_c = {}
+    sim_ber_device(mk(), np.array([4.0, 4.5], dtype=np.float32), 512, 12, target_block_errs=10 ** 6, verbose=False, stats=st_c)
+    assert st_c["counted"] == 24 and st_c["queued"] == 24
+    from types import SimpleNamespace
+    pes = np.array([0.5, 0.4, 0.3], dtype=np.float32)
+    mb = lambda: System_BEC_model(SimpleNamespace(n=n, k=k), PolarEncoder(fp, n, None), SC_Dec(fp, n), seed=23)
+    r_dev = sim_ber(mb(), pes, 2000, 3, target_block_errs=50, verbose=False)
+    r_host = sim_ber(mb(), pes, 2000, 3, target_block_errs=50, verbose=False, on_device=False)
+    assert torch.equal(r_dev[0], r_host[0]) and torch.equal(r_dev[1], r_host[1])
+    assert 0.0 < float(r_dev[1][2]) < float(r_dev[1][0]) <= 1.0
+
+
 def test_on_device_loop_with_process_group_of_one():
     """The sharded path (stream-ordered NCCL all-reduce of the 4 counters before polar_mc_control) with world size 1."""
     torch, dk, po, co, dev = _env()

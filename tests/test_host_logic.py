@@ -244,3 +244,49 @@ def test_main_cli_fallback_parser_follows_the_annotations():
     assert c.algos == ["sc", "scl"] and c.verbose is True
     d = m.parse_config([])
     assert (d.k, d.n, d.bs, d.snr_end, d.seed) == (32, 64, 3, 5, 42)
+
+
+def test_stop_predictor_of_the_device_monte_carlo_loop():
+    """my_sn/sim.py::StopPredictor: look-ahead is skipped only when the counters seen so far say, with margin, that the
+    queued iterations reach a target; it can never change a result (the control kernel ignores surplus iterations)."""
+    from my_sn.sim import StopPredictor
+    p = StopPredictor(None, 1000, 16)
+    assert p.speculate(1)                                  # nothing known, no previous point: queue ahead
+    p.observe(1, 10 ** 7, 65536); p.end_point()            # configs[3]: every block in error at the first point
+    p.start_point()
+    assert not p.speculate(1)                              # a tenth of 65536 still clears 1000 with margin: wait for the flag
+    p.observe(1, 10 ** 6, 17000); p.end_point()
+    p.start_point()
+    assert not p.speculate(1)
+    p.observe(1, 2000, 150); p.end_point()                 # waterfall region: 150 errors per iteration
+    p.start_point()
+    assert p.speculate(1)                                  # 15 predicted: far from the target
+    p.observe(1, 900, 60)
+    assert p.speculate(2)
+    p.observe(15, 13000, 900)
+    assert p.speculate(15) and not p.speculate(16)         # max_mc_iter caps the queue
+    p.observe(6, 50000, 900)
+    assert p.speculate(7)                                  # 900 + 150 = 1050 < 1000 + 3 sigma: not confident, keep the GPU busy
+    p.observe(6, 50000, 990)
+    assert not p.speculate(7)                              # 990 + 165 = 1155 clears the target with margin
+    q = StopPredictor(5000, None, 4)
+    q.observe(1, 4000, 1)
+    assert not q.speculate(2)                              # 8000 predicted bit errors against 5000
+    q = StopPredictor(None, None, 3)
+    q.observe(1, 1, 1)
+    assert q.speculate(1) and q.speculate(2) and not q.speculate(3)
+
+
+def test_encoder_rejects_non_arikan_generator():
+    """PolarEncoder applies the Arikan butterfly; any other G must raise instead of encoding something else."""
+    import torch
+    from d_kernels import F2, gen_arikan
+    from polar.enc import PolarEncoder
+    from polar.froze import get_Kern_frozen_bits
+    assert F2.device.type == "cpu"                         # kernel matrices stay on the host (no CUDA context at import)
+    G, _, fp = get_Kern_frozen_bits(64, 32, F2)
+    assert PolarEncoder(fp, 64, G).G_ is None and PolarEncoder(fp, 64, None).k == 32
+    bad = G.clone(); bad[5, 2] = 1
+    for g in (bad, G.t().contiguous(), gen_arikan(torch.tensor([[1., 1.], [0., 1.]]), 6), G[:32, :32]):
+        with pytest.raises(AssertionError):
+            PolarEncoder(fp, 64, g)
