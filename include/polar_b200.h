@@ -11,10 +11,11 @@
  *  - Every pointer named d_* is a DEVICE pointer into caller-owned memory (e.g. a torch CUDA
  *    tensor's data_ptr()); h_* is a HOST pointer.  No torch types cross this boundary.
  *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device entry
- *    points only enqueue work: they never synchronise and never allocate -- with one exception: the first SC
- *    decode of n >= 1024 on a device allocates that device's stage scratch (one slot per SM, 76 MB on a 148-SM
- *    part, kept for the life of the process; csrc/polar_sc4.cu).  If that allocation is impossible (e.g. during
- *    stream capture) the kernel runs without the scratch.
+ *    points only enqueue work: they never synchronise, never allocate and never read the environment, so they
+ *    are safe under stream capture.  The one allocation the kernels need -- the SC stage scratch (one slot per SM,
+ *    76 MB on a 148-SM part, csrc/polar_sc4.cu) -- is made by polar_init(device), which a caller runs once per
+ *    device before decoding (the Python loader does it when it builds a code's device tables); an SC decode of
+ *    n >= 1024 on a device that was not initialised returns POLAR_EINVAL with a message saying so.
  *  - Bit packing: bit (i % 32) of 32-bit word (i / 32) holds position i (LSB first); a row of n
  *    positions occupies POLAR_WORDS(n) = max(1, n/32) words.
  *  - Logits follow the reference decoder input: ln P(1)/P(0), fp32, row-major [B, n]
@@ -44,6 +45,14 @@ extern "C" {
 #define POLAR_WORDS(n) ((n) < 32 ? 1 : (n) / 32)
 
 const char *polar_last_error(void);
+/* One-time per-device set-up (may allocate and synchronise; idempotent, thread safe, restores the current device):
+ * queries the device and allocates the SC stage scratch.  Required before polar_sc_decode_* of n >= 1024; the
+ * host-buffer entry points call it themselves. */
+int polar_init(int device);
+/* Tuning / test options, by the name of the POLAR_* environment variable they shadow (an explicit override wins over
+ * the environment; the environment is looked up once per option, never on the launch path).  Not needed by callers. */
+int polar_set_option(const char *name, int value);
+void polar_clear_options(void);
 /* library / device info: writes "polar_b200 <version> sm_100a ..." */
 const char *polar_version(void);
 /* number of kernels this library has launched in the calling process (bench.py: gpu_launches) */
@@ -191,6 +200,16 @@ int polar_sc_decode_host(const float *h_logit, const uint32_t *h_frozen_mask, in
 int polar_scl_decode_host(const float *h_logit, const uint32_t *h_frozen_mask, int n, int L, int64_t B,
                           uint32_t *h_best_packed, double *h_pm_sorted_or_null,
                           const uint32_t *h_crc_rows_or_null, int crc_len, int device);
+/* The same with the tensor the reference's forward() returns: h_u_info_f32 [B, k] fp32 0./1. at ascending h_info_pos
+ * (polar_sc.py:127-133, polar_scl.py:224-234).  Either output may be NULL (not both).  This is what SC_Dec.forward /
+ * SCL_Dec.forward call for a CPU tensor.  Pageable caller buffers are staged through page-locked memory by a few
+ * host threads (POLAR_HOST_COPY_THREADS, default 4); page-locked ones are DMA'd directly. */
+int polar_sc_decode_host_f32(const float *h_logit, const uint32_t *h_frozen_mask, int n, int64_t B,
+                             uint32_t *h_u_packed_or_null, float *h_u_info_f32_or_null, const int32_t *h_info_pos, int k,
+                             int device);
+int polar_scl_decode_host_f32(const float *h_logit, const uint32_t *h_frozen_mask, int n, int L, int64_t B,
+                              uint32_t *h_best_packed_or_null, float *h_u_info_f32_or_null, const int32_t *h_info_pos, int k,
+                              double *h_pm_sorted_or_null, const uint32_t *h_crc_rows_or_null, int crc_len, int device);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,7 @@
 // polar_internal.h -- host-side plumbing shared by the C-ABI translation units.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -12,9 +13,31 @@ namespace polar {
 
 int set_error(int code, const char *fmt, ...);      // stores thread-local text, returns code
 void count_launch(int n = 1);                        // gpu_launches accounting
-int env_int(const char *name, int dflt);             // tuning overrides (POLAR_*), read per call
 int device_sm_count();
 int device_max_smem_optin();
+
+// Tuning / test options (POLAR_* names).  An option is an explicit override set through polar_set_option(), else the
+// environment variable of the same name, else the call site's default.  The environment is NOT read on the launch path:
+// every call site caches its lookup and repeats it only after polar_set_option() / polar_clear_options() bumped the
+// generation counter, so a decode costs one relaxed atomic load per option.
+struct OptSlot { std::atomic<unsigned> gen{0}; std::atomic<int> has{0}; std::atomic<int> val{0}; };
+extern std::atomic<unsigned> g_opt_gen;
+bool opt_lookup(const char *name, int *value);
+inline int opt_get(OptSlot &s, const char *name, int dflt) {
+  const unsigned g = g_opt_gen.load(std::memory_order_acquire);
+  if (s.gen.load(std::memory_order_relaxed) != g) {
+    int v = 0;
+    const bool has = opt_lookup(name, &v);
+    s.val.store(v, std::memory_order_relaxed); s.has.store(has ? 1 : 0, std::memory_order_relaxed);
+    s.gen.store(g, std::memory_order_release);
+  }
+  return s.has.load(std::memory_order_relaxed) ? s.val.load(std::memory_order_relaxed) : dflt;
+}
+#define env_int(NAME, DFLT) ([&]() -> int { static ::polar::OptSlot s__; return ::polar::opt_get(s__, NAME, (DFLT)); }())
+
+// polar_sc4.cu: per-device stage scratch, allocated by polar_init()
+int sc4_scratch_init(int device);
+float *sc4_scratch();                                // nullptr until polar_init(device) ran
 
 // polar_sc3.cu: SC decoder with compile-time tree geometry (n in [128, 8192])
 int launch_sc3(const float *logit, const uint32_t *fmask, int n, int64_t B, uint32_t *u_packed, float *u_info,

@@ -16,6 +16,7 @@
 //     storage); stages 7 and 6 plus the partial-sum words in shared memory (916 B per codeword).
 //   * only partial sums are produced on the serial path; the decisions are recovered once per codeword as
 //     u = T(x_hat).
+#include <atomic>
 #include <mutex>
 
 #include "polar_common.cuh"
@@ -656,29 +657,40 @@ __global__ void nsmid_kernel(unsigned *out) {
   asm volatile("mov.u32 %0, %%nsmid;" : "=r"(v));
   *out = v;
 }
-// Per-device stage scratch of the virtual-stage kernels (n >= 1024), allocated on first use and kept for the life of
-// the process: %nsmid slots of kSc4ScratchPerSm (76 MB on a 148-SM part) -- small enough to stay resident in the L2.
+std::mutex g_scr_mu;
+std::atomic<float *> g_scr_buf[64];
+
+}  // namespace
+
+// Per-device stage scratch of the virtual-stage kernels (n >= 1024): %nsmid slots of kSc4ScratchPerSm (76 MB on a
+// 148-SM part) -- small enough to stay resident in the L2.  Allocated once by polar_init(device) (which may allocate and
+// synchronise; the decode entry points never do) and kept for the life of the process.
+int sc4_scratch_init(int device) {
+  if (device < 0 || device >= 64) return set_error(POLAR_EINVAL, "init: bad device %d", device);
+  std::lock_guard<std::mutex> lk(g_scr_mu);
+  if (g_scr_buf[device].load(std::memory_order_acquire)) return POLAR_OK;
+  unsigned *d_n = nullptr, h_n = 0;
+  POLAR_CUDA(cudaMalloc(&d_n, sizeof(unsigned)));
+  nsmid_kernel<<<1, 1>>>(d_n);
+  const cudaError_t e = cudaMemcpy(&h_n, d_n, sizeof(unsigned), cudaMemcpyDeviceToHost);
+  cudaFree(d_n);
+  if (e != cudaSuccess) return set_error(POLAR_ECUDA, "init: %s", cudaGetErrorString(e));
+  if (h_n == 0 || h_n > 1024) return set_error(POLAR_ECUDA, "init: implausible %%nsmid = %u", h_n);
+  void *p = nullptr;
+  if (cudaMalloc(&p, (size_t)h_n * kSc4ScratchPerSm) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return set_error(POLAR_ENOMEM, "init: cudaMalloc of the %zu-byte SC stage scratch failed", (size_t)h_n * kSc4ScratchPerSm);
+  }
+  g_scr_buf[device].store((float *)p, std::memory_order_release);
+  return POLAR_OK;
+}
 float *sc4_scratch() {
-  static std::mutex mu;
-  static float *buf[64];
-  static bool tried[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  std::lock_guard<std::mutex> lk(mu);
-  if (!tried[dev]) {
-    tried[dev] = true;
-    unsigned *d_n = nullptr, h_n = 0;
-    if (cudaMalloc(&d_n, sizeof(unsigned)) == cudaSuccess) {
-      nsmid_kernel<<<1, 1>>>(d_n);
-      if (cudaMemcpy(&h_n, d_n, sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) h_n = 0;
-      cudaFree(d_n);
-    }
-    void *p = nullptr;
-    if (h_n > 0 && h_n <= 1024 && cudaMalloc(&p, (size_t)h_n * kSc4ScratchPerSm) == cudaSuccess) buf[dev] = (float *)p;
-    else (void)cudaGetLastError();
-  }
-  return buf[dev];
+  return g_scr_buf[dev].load(std::memory_order_acquire);
 }
+
+namespace {
 
 template <int M, int MODE>
 int launch_sc4_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t *u_packed, float *u_info,
@@ -706,6 +718,8 @@ int launch_sc4_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t 
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
   float *scratch = (MODE == 2 && env_int("POLAR_SC4_SCRATCH", 1)) ? sc4_scratch() : nullptr;
+  if (MODE == 2 && env_int("POLAR_SC4_SCRATCH", 1) && !scratch)
+    return set_error(POLAR_EINVAL, "sc: n=%d needs the per-device stage scratch -- call polar_init(device) once before decoding", 1 << M);
   kern<<<(unsigned)grid, warps * 32, smem, st>>>(logit, fmask, B, nbatches, env_int("POLAR_SC4_PREFETCH", 0),
                                                   env_int("POLAR_SC4_HINTS", 2), env_int("POLAR_SC3_DBG", 0), scratch, env_int("POLAR_SC4_DISCARD", 1), u_packed, u_info, info_pos, k);
   count_launch();

@@ -134,13 +134,17 @@ class SCL_Dec(nn.Module):
       if rows is None:
         rows = self._crc_rows[str(dev)] = tc.from_numpy(self._crc_rows_np.view(np.int32).copy()).to(dev)
       ln = self._k_crc
-    res = dk.scl_decode(inputs, tables, self._list_size, crc_rows=rows, crc_len=ln, want_info=True, want_pm=True,
-                        boxplus=self._boxplus)
-    self.msg_pm = res["pm"]
+    if not inputs.is_cuda and not self._boxplus:     # CPU tensor: chunked, overlapped H2D / decode / D2H inside one call
+      u_info, self.msg_pm = dk.scl_decode_host(inputs, tables, self._list_size,
+                                               crc_rows_np=self._crc_rows_np if self._use_crc else None, crc_len=ln)
+    else:
+      res = dk.scl_decode(inputs, tables, self._list_size, crc_rows=rows, crc_len=ln, want_info=True, want_pm=True,
+                          boxplus=self._boxplus)
+      u_info, self.msg_pm = res["u_info"], res["pm"]
     output_shape = list(inputs.shape)
     output_shape[-1] = self.k
     output_shape[0] = -1
-    out = res["u_info"].reshape(output_shape).to(self.output_dtype)   # CRC bits stay in the output (dec.py:527)
+    out = u_info.reshape(output_shape).to(self.output_dtype)          # CRC bits stay in the output (dec.py:527)
     if self._return_crc_status:
       raise Exception('not implement...')                              # dec.py:534-535
     return out if inputs.is_cuda else out.to(inputs.device)

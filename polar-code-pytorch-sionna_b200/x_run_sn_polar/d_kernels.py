@@ -47,6 +47,9 @@ _SIGNATURES = {
   "polar_last_error": (ctypes.c_char_p, []),
   "polar_version": (ctypes.c_char_p, []),
   "polar_launch_count": (ctypes.c_ulonglong, []),
+  "polar_init": (_i32, [_i32]),
+  "polar_set_option": (_i32, [ctypes.c_char_p, _i32]),
+  "polar_clear_options": (None, []),
   "polar_sc_decode_f32": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _i32, _vp]),
   "polar_sc_decode_boxplus_f32": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _i32, _vp]),
   "polar_scl_workspace_bytes": (_sz, [_i32, _i32, _i64]),
@@ -69,6 +72,8 @@ _SIGNATURES = {
   "polar_unpack_info_f32": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp]),
   "polar_sc_decode_host": (_i32, [_vp, _vp, _i32, _i64, _vp, _i32]),
   "polar_scl_decode_host": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _i32, _i32]),
+  "polar_sc_decode_host_f32": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _i32, _i32]),
+  "polar_scl_decode_host_f32": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32]),
 }
 
 
@@ -148,12 +153,34 @@ def frozen_mask_words(frozen_pos, n):
   return w[:words(n)].copy()
 
 
+_INITIALISED = set()
+
+
+def init_device(dev):
+  """polar_init(device) once per device: the only call of the library that allocates on its own (SC stage scratch)."""
+  idx = dev.index if dev.index is not None else tc.cuda.current_device()
+  if idx not in _INITIALISED:
+    check(lib().polar_init(int(idx)))
+    _INITIALISED.add(idx)
+  return idx
+
+
+def set_option(name, value):
+  """Tuning / test override of a POLAR_* option (include/polar_b200.h: polar_set_option)."""
+  check(lib().polar_set_option(name.encode(), int(value)))
+
+
+def clear_options():
+  lib().polar_clear_options()
+
+
 class CodeTables:
   """Device-resident description of one (frozen set, n) code, shared by encoder/decoders/front end."""
 
   def __init__(self, frozen_pos, n, dev):
     self.n = int(n)
     self.dev = dev
+    init_device(dev)
     fp = to_numpy_pos(frozen_pos)
     self.info_pos_np = np.setdiff1d(np.arange(self.n), fp)          # ascending (polar_sc.py:19)
     self.k = int(self.info_pos_np.shape[0])
@@ -237,6 +264,43 @@ def scl_decode(logits, tables, list_size, crc_rows=None, crc_len=0, want_info=Tr
                                  ptr(tables.info_pos), tables.k, ptr(out["pm"]), ptr(out["list"]),
                                  ptr(crc_rows), int(crc_len), ptr(ws), need, stream_ptr(dev)))
   return out
+
+
+def _host_logits(x, n):
+  """CPU tensor -> contiguous fp32 [B, n] host tensor (no copy when it already is one)."""
+  x = x.detach().reshape(-1, n)
+  if x.dtype != tc.float32:
+    x = x.to(tc.float32)
+  return x.contiguous()
+
+
+def sc_decode_host(logits_cpu, tables, boxplus=False):
+  """SC_Dec.forward on a CPU tensor: polar_sc_decode_host_f32 (chunked H2D -> decode -> D2H on two streams inside the call).
+  Returns the [B, k] fp32 API tensor in page-locked host memory (torch's caching host allocator recycles it)."""
+  if boxplus:      # the boxplus decoders have no host-buffer entry point: plain copy, decode, copy back
+    u, _ = sc_decode(logits_cpu, tables, want_info=True, boxplus=True)
+    return u.cpu()
+  x = _host_logits(logits_cpu, tables.n)
+  B = x.shape[0]
+  out = tc.empty((B, tables.k), dtype=tc.float32, pin_memory=B > 0)
+  pos = tables.info_pos_np.astype(np.int32)
+  check(lib().polar_sc_decode_host_f32(x.data_ptr(), tables.mask_np.ctypes.data, tables.n, B, None, out.data_ptr(),
+                                       pos.ctypes.data, tables.k, init_device(tables.dev)))
+  return out
+
+
+def scl_decode_host(logits_cpu, tables, list_size, crc_rows_np=None, crc_len=0, want_pm=True):
+  """SCL_Dec.forward on a CPU tensor: polar_scl_decode_host_f32.  -> (u_info [B,k] fp32 pinned, pm [B,L] fp64 | None)."""
+  x = _host_logits(logits_cpu, tables.n)
+  B, L = x.shape[0], int(list_size)
+  out = tc.empty((B, tables.k), dtype=tc.float32, pin_memory=B > 0)
+  pm = tc.empty((B, L), dtype=tc.float64, pin_memory=B > 0) if want_pm else None
+  pos = tables.info_pos_np.astype(np.int32)
+  rows = None if crc_rows_np is None else np.ascontiguousarray(crc_rows_np, dtype=np.uint32)
+  check(lib().polar_scl_decode_host_f32(x.data_ptr(), tables.mask_np.ctypes.data, tables.n, L, B, None, out.data_ptr(),
+                                        pos.ctypes.data, tables.k, pm.data_ptr() if want_pm else None,
+                                        rows.ctypes.data if rows is not None else None, int(crc_len), init_device(tables.dev)))
+  return out, pm
 
 
 def encode_f32(u, tables, want_packed=False):

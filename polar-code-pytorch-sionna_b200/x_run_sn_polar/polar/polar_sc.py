@@ -42,9 +42,11 @@ class SC_Dec(nn.Module):
     assert len(inputs.shape) > 1
     dev = inputs.device if inputs.is_cuda else dk.cuda_device(self.device)
     tables = dk.code_tables(self.frozen_pos, self.n, dev)
-    u_hat, _ = dk.sc_decode(inputs, tables, want_info=True)
+    if inputs.is_cuda:
+      u_hat, _ = dk.sc_decode(inputs, tables, want_info=True)
+    else:         # CPU tensor in -> CPU tensor out (the reference's boundary): chunked, overlapped H2D / decode / D2H
+      u_hat = dk.sc_decode_host(inputs, tables)
     output_shape = list(inputs.shape)
     output_shape[-1] = self.k
     output_shape[0] = -1
-    out = u_hat.reshape(output_shape).to(dtype=self.output_dtype)
-    return out if inputs.is_cuda else out.to(inputs.device)
+    return u_hat.reshape(output_shape).to(dtype=self.output_dtype)

@@ -57,10 +57,12 @@ class SCL_Dec(nn.Module):
     assert inputs.dim() > 1
     dev = inputs.device if inputs.is_cuda else dk.cuda_device(self.device)
     tables = dk.code_tables(self._frozen_pos, self._n, dev)
-    res = dk.scl_decode(inputs, tables, self._list_size, want_info=True, want_pm=True)
-    self.msg_pm = res["pm"]                      # [B, L] ascending (reference keeps [B, 2L] duplicates)
+    if inputs.is_cuda:
+      res = dk.scl_decode(inputs, tables, self._list_size, want_info=True, want_pm=True)
+      u_info, self.msg_pm = res["u_info"], res["pm"]   # [B, L] ascending (reference keeps [B, 2L] duplicates)
+    else:         # CPU tensor in -> CPU tensor out (the reference's boundary): chunked, overlapped H2D / decode / D2H
+      u_info, self.msg_pm = dk.scl_decode_host(inputs, tables, self._list_size)
     output_shape = list(inputs.shape)
     output_shape[-1] = self.k
     output_shape[0] = -1
-    out = res["u_info"].reshape(output_shape).to(self.output_dtype)
-    return out if inputs.is_cuda else out.to(inputs.device)
+    return u_info.reshape(output_shape).to(self.output_dtype)

@@ -37,3 +37,12 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _clear_polar_options():
+    """tests set tuning options with util.set_opt (polar_set_option); none may leak into the next test"""
+    yield
+    dk = sys.modules.get("d_kernels")
+    if dk is not None and getattr(dk, "_lib", None) is not None:
+        dk.clear_options()

@@ -172,7 +172,7 @@ def test_scl_known_ill_conditioned_codeword():
     got = unpack_words(res["u_packed"].cpu().numpy(), n)
     pm = res["pm"].cpu().numpy()
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
-    if os.path.isdir(out_dir):      # kept as a CPU fixture (tests/golden/scl_illcond_1024_L8.npz, tests/test_oracle_golden.py)
+    if os.path.isdir(out_dir):      # kept as a CPU fixture (tests/golden/illcond_scl_1024_L8.npz, tests/test_oracle_golden.py)
         np.savez(os.path.join(out_dir, "cw122257.npz"), logits=xh, gpu_best=got, gpu_pm=pm, c_best=u_ref[:, 0], c_pm=pm_ref)
     bad = np.nonzero((got != u_ref[:, 0]).any(axis=1))[0]
     _check_mismatches(po, "codeword 122257", bad, xh, fz, L, got, pm[:, 0], u_ref[:, 0], lambda u, p: u[:, 0], cap=1)

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from util import golden, golden_names, unpack_words, pack_words, awgn_logits
+from util import golden, golden_names, unpack_words, pack_words, awgn_logits, set_opt
 
 pytestmark = pytest.mark.gpu
 
@@ -201,7 +201,7 @@ def test_my_sn_encoder_and_parity_check():
 @pytest.mark.parametrize("n,B,chunk_mb", [(1024, 5000, 1), (64, 100000, 1), (2048, 700, 128)])
 def test_host_buffer_entry_points_match_device_path(n, B, chunk_mb, monkeypatch):
     torch, dk, po, co, dev = _env()
-    monkeypatch.setenv("POLAR_HOST_CHUNK_MB", str(chunk_mb))     # several chunks -> exercises the 2-stream pipeline
+    set_opt("POLAR_HOST_CHUNK_MB", str(chunk_mb))     # several chunks -> exercises the 2-stream pipeline
     k = n // 2
     fp = po.rm_frozen_pos(n, n - k)
     tables = dk.code_tables(fp, n, dev)

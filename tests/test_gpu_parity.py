@@ -4,7 +4,7 @@ Bar: bit-exact decisions; SCL path metrics within 1e-5 relative (BASELINE.json n
 import numpy as np
 import pytest
 
-from util import golden, golden_names, unpack_words, pack_words, awgn_logits
+from util import golden, golden_names, unpack_words, pack_words, awgn_logits, set_opt
 
 pytestmark = pytest.mark.gpu
 PM_RTOL = 1e-5   # north_star tolerance for SCL path metrics
@@ -53,8 +53,8 @@ def test_sc_all_codewords_per_warp_variants(cw, monkeypatch):
     from oracle import polar_oracle as po, c_oracle as co
     dk = _dk()
     n, k, B = 256, 128, 1111
-    monkeypatch.setenv("POLAR_SC_MODE", "0")           # warp-per-CW-codewords mapping
-    monkeypatch.setenv("POLAR_SC_CW", str(cw))
+    set_opt("POLAR_SC_MODE", "0")           # warp-per-CW-codewords mapping
+    set_opt("POLAR_SC_CW", str(cw))
     fp = po.rm_frozen_pos(n, n - k)
     _, logits = awgn_logits(np.random.default_rng(cw), n, k, fp, B, 2.0)
     ref = co.sc_decode_full(logits, po.frozen_vec(fp, n))
@@ -69,9 +69,9 @@ def test_sc_cta_mapping_variants(ctas, threads, n, monkeypatch):
     from oracle import polar_oracle as po, c_oracle as co
     dk = _dk()
     k, B = n // 2, 3001
-    monkeypatch.setenv("POLAR_SC_MODE", "1")           # CTA-cooperative mapping (default)
-    monkeypatch.setenv("POLAR_SC_CTAS", str(ctas))
-    monkeypatch.setenv("POLAR_SC_THREADS", str(threads))
+    set_opt("POLAR_SC_MODE", "1")           # CTA-cooperative mapping (default)
+    set_opt("POLAR_SC_CTAS", str(ctas))
+    set_opt("POLAR_SC_THREADS", str(threads))
     fp = po.rm_frozen_pos(n, n - k)
     _, logits = awgn_logits(np.random.default_rng(ctas), n, k, fp, B, 3.0)
     logits[::9] = np.round(logits[::9])
@@ -90,9 +90,9 @@ def test_sc3_mapping_variants(cw, ctas, n, monkeypatch):
     from oracle import polar_oracle as po, c_oracle as co
     dk = _dk()
     k, B = n // 2, 2000 if n <= 2048 else 300
-    monkeypatch.setenv("POLAR_SC_MODE", "2")
-    monkeypatch.setenv("POLAR_SC_CTA_CW", str(cw))
-    monkeypatch.setenv("POLAR_SC_CTAS", str(ctas))
+    set_opt("POLAR_SC_MODE", "2")
+    set_opt("POLAR_SC_CTA_CW", str(cw))
+    set_opt("POLAR_SC_CTAS", str(ctas))
     fp = po.rm_frozen_pos(n, n - k)
     _, logits = awgn_logits(np.random.default_rng(cw + n), n, k, fp, B, 3.0)
     logits[::9] = np.round(logits[::9])
@@ -111,8 +111,8 @@ def test_sc4_warp_autonomous_variants(warps, n, B, monkeypatch):
     from oracle import polar_oracle as po, c_oracle as co
     dk = _dk()
     k = n // 2
-    monkeypatch.setenv("POLAR_SC_MODE", "3")
-    monkeypatch.setenv("POLAR_SC_WARPS_SM", str(warps))
+    set_opt("POLAR_SC_MODE", "3")
+    set_opt("POLAR_SC_WARPS_SM", str(warps))
     fp = po.rm_frozen_pos(n, n - k)
     _, logits = awgn_logits(np.random.default_rng(warps + n), n, k, fp, B, 3.0)
     logits[::9] = np.round(logits[::9])
@@ -130,7 +130,7 @@ def test_sc3_extreme_frozen_patterns(n, mode, monkeypatch):
     import torch
     from oracle import polar_oracle as po, c_oracle as co
     dk = _dk()
-    monkeypatch.setenv("POLAR_SC_MODE", str(mode))
+    set_opt("POLAR_SC_MODE", str(mode))
     B = 333
     rng = np.random.default_rng(n)
     logits = (rng.standard_normal((B, n)) * 4).astype(np.float32)
@@ -160,10 +160,10 @@ def test_sc_stage_scratch_is_transparent(n, B, monkeypatch):
     fp = po.rm_frozen_pos(n, n - k)
     tables = dk.code_tables(fp, n, dev)
     _, _, x = dk.awgn_frontend(tables, B, po.ebnodb2no(3.0, 2, k / n), 31337)
-    monkeypatch.setenv("POLAR_SC4_SCRATCH", "0")
+    set_opt("POLAR_SC4_SCRATCH", "0")
     _, ref = dk.sc_decode(x, tables, want_info=False, want_packed=True)
     torch.cuda.synchronize()
-    monkeypatch.setenv("POLAR_SC4_SCRATCH", "1")
+    set_opt("POLAR_SC4_SCRATCH", "1")
     _, got = dk.sc_decode(x, tables, want_info=False, want_packed=True)
     assert torch.equal(got, ref)
     # two streams, small launches that do not fill the GPU -> the two kernels really overlap
@@ -355,7 +355,7 @@ def test_scl3_equals_scl2_lists_and_path_metrics(n, L, B, ebno, monkeypatch):
     _, _, x = dk.awgn_frontend(tables, B, po.ebnodb2no(ebno, 2, k / n), 99 + n + L)
     out = {}
     for mode in ("1", "2"):
-        monkeypatch.setenv("POLAR_SCL_MODE", mode)
+        set_opt("POLAR_SCL_MODE", mode)
         out[mode] = dk.scl_decode(x, tables, L, want_packed=True, want_info=True, want_pm=True, want_list=True)
         torch.cuda.synchronize()
     for key in ("u_packed", "u_info", "list"):

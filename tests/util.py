@@ -40,3 +40,9 @@ def awgn_logits(rng, n, k, frozen_pos, B, ebno_db):
     no = po.ebnodb2no(ebno_db, 2, k / n)
     y = (1.0 - 2.0 * c) / np.sqrt(2.0) + np.sqrt(no / 2.0) * rng.standard_normal((B, n))
     return u, (-2.0 * np.sqrt(2.0) * y / no).astype(np.float32)
+
+
+def set_opt(name, value):
+    """Override a POLAR_* tuning option for the current test (polar_set_option; undone by conftest's autouse fixture)."""
+    import d_kernels as dk
+    dk.set_option(name, int(value))

@@ -39,10 +39,10 @@ def main():
         B = int(sys.argv[3]) if len(sys.argv) > 3 else (1 << 28) // n
         _, _, x = dk.awgn_frontend(tables, B, no, 1234)
         up = torch.empty((B, dk.words(n)), dtype=torch.int32, device=dev)
-        os.environ["POLAR_SC_MODE"] = "1"
+        dk.set_option("POLAR_SC_MODE", int("1"))
         for ctas in [int(v) for v in os.environ.get("CTAS", "1,2,3,4,6").split(",")]:
             for thr in [int(v) for v in os.environ.get("THREADS", "64,128,256").split(",")]:
-                os.environ["POLAR_SC_CTAS"] = str(ctas); os.environ["POLAR_SC_THREADS"] = str(thr)
+                dk.set_option("POLAR_SC_CTAS", int(str(ctas))); dk.set_option("POLAR_SC_THREADS", int(str(thr)))
                 f = lambda: dk.check(dk.lib().polar_sc_decode_f32(dk.ptr(x), dk.ptr(tables.frozen_mask), n, B, dk.ptr(up), None, None, 0, dk.stream_ptr(dev)))
                 best, med = timeit(f)
                 print("SC-CTA n=%d B=%d ctas/SM=%d threads=%3d: %8.3f ms  %.3e cw/s  %.1f Gbit/s info  HBM-frac %.3f" %
@@ -52,9 +52,9 @@ def main():
         B = int(sys.argv[3]) if len(sys.argv) > 3 else (1 << 28) // n
         _, _, x = dk.awgn_frontend(tables, B, no, 1234)
         up = torch.empty((B, dk.words(n)), dtype=torch.int32, device=dev)
-        os.environ["POLAR_SC_MODE"] = "3"
+        dk.set_option("POLAR_SC_MODE", int("3"))
         for w in [int(v) for v in os.environ.get("WARPS", "0").split(",")]:
-            os.environ["POLAR_SC_WARPS_SM"] = str(w)
+            dk.set_option("POLAR_SC_WARPS_SM", int(str(w)))
             f = lambda: dk.check(dk.lib().polar_sc_decode_f32(dk.ptr(x), dk.ptr(tables.frozen_mask), n, B, dk.ptr(up), None, None, 0, dk.stream_ptr(dev)))
             best, med = timeit(f)
             if os.environ.get("POLAR_SC3_DBG") == "1":
@@ -69,12 +69,12 @@ def main():
         B = int(sys.argv[3]) if len(sys.argv) > 3 else (1 << 28) // n
         _, _, x = dk.awgn_frontend(tables, B, no, 1234)
         up = torch.empty((B, dk.words(n)), dtype=torch.int32, device=dev)
-        os.environ["POLAR_SC_MODE"] = "2"
+        dk.set_option("POLAR_SC_MODE", int("2"))
         for cw in [int(v) for v in os.environ.get("CWS", "32").split(",")]:
             for ctas in [int(v) for v in os.environ.get("CTAS", "0,2,3,4").split(",")]:
                 for thr in [128]:
-                    os.environ["POLAR_SC_CTAS"] = str(ctas); os.environ["POLAR_SC_THREADS"] = str(thr)
-                    os.environ["POLAR_SC_CTA_CW"] = str(cw)
+                    dk.set_option("POLAR_SC_CTAS", int(str(ctas))); dk.set_option("POLAR_SC_THREADS", int(str(thr)))
+                    dk.set_option("POLAR_SC_CTA_CW", int(str(cw)))
                     f = lambda: dk.check(dk.lib().polar_sc_decode_f32(dk.ptr(x), dk.ptr(tables.frozen_mask), n, B, dk.ptr(up), None, None, 0, dk.stream_ptr(dev)))
                     best, med = timeit(f)
                     if os.environ.get("POLAR_SC3_DBG") == "1":
@@ -87,13 +87,13 @@ def main():
                     print("SC3 n=%d B=%d cw=%d ctas/SM=%d threads=%3d bwdiv=%s: %8.3f ms  %.3e cw/s  %.1f Gbit/s info  HBM-frac %.3f" %
                           (n, B, cw, ctas, thr, os.environ.get("POLAR_SC3_BWDIV", "sms"), best, B / best * 1e3, B / best * 1e3 * k / 1e9, B / best * 1e3 * (4 * n + k / 8) / 6552.3e9), flush=True)
     elif what == "sc":
-        os.environ["POLAR_SC_MODE"] = "0"
+        dk.set_option("POLAR_SC_MODE", int("0"))
         B = int(sys.argv[3]) if len(sys.argv) > 3 else (1 << 28) // n
         _, _, x = dk.awgn_frontend(tables, B, no, 1234)
         up = torch.empty((B, dk.words(n)), dtype=torch.int32, device=dev)
         for cw in [int(v) for v in os.environ.get("CWS", "2,4,8,16,32").split(",")]:
             for warps in [int(v) for v in os.environ.get("WARPS", "1,2,4").split(",")]:
-                os.environ["POLAR_SC_CW"] = str(cw); os.environ["POLAR_SC_WARPS"] = str(warps)
+                dk.set_option("POLAR_SC_CW", int(str(cw))); dk.set_option("POLAR_SC_WARPS", int(str(warps)))
                 try:
                     f = lambda: dk.check(dk.lib().polar_sc_decode_f32(dk.ptr(x), dk.ptr(tables.frozen_mask), n, B, dk.ptr(up), None, None, 0, dk.stream_ptr(dev)))
                     best, med = timeit(f)
@@ -107,7 +107,7 @@ def main():
         _, _, x = dk.awgn_frontend(tables, B, no, 1234)
         for kb in [int(v) for v in os.environ.get("KBS", "4").split(",")]:
             for warps in [int(v) for v in os.environ.get("WARPS", "1,2,4").split(",")]:
-                os.environ["POLAR_SCL_SMEM_KB"] = str(kb); os.environ["POLAR_SCL_WARPS"] = str(warps)
+                dk.set_option("POLAR_SCL_SMEM_KB", int(str(kb))); dk.set_option("POLAR_SCL_WARPS", int(str(warps)))
                 try:
                     f = lambda: dk.scl_decode(x, tables, L, want_packed=True, want_info=False)
                     best, med = timeit(f, iters=3, warm=1)
@@ -128,15 +128,15 @@ def main():
         B = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 15
         ebno = float(os.environ.get("EBNO", "3.0"))
         _, _, x = dk.awgn_frontend(tables, B, po.ebnodb2no(ebno, 2, k / n), 1234)
-        os.environ["POLAR_SCL_MODE"] = "1"
+        dk.set_option("POLAR_SCL_MODE", int("1"))
         ref = dk.scl_decode(x, tables, L, want_packed=True, want_info=False, want_pm=True, want_list=True)
         torch.cuda.synchronize()
         best, med = timeit(lambda: dk.scl_decode(x, tables, L, want_packed=True, want_info=False), iters=3, warm=1)
         print("scl2 L=%d n=%d B=%d: %8.3f ms  %.3e cw/s  %.3f Gbit/s info" % (L, n, B, best, B / best * 1e3, B / best * 1e3 * k / 1e9), flush=True)
-        os.environ["POLAR_SCL_MODE"] = "2"
+        dk.set_option("POLAR_SCL_MODE", int("2"))
         for ss in [int(v) for v in os.environ.get("SS", "5,6,7").split(",")]:
             for ctas in [int(v) for v in os.environ.get("CTAS", "0").split(",")]:
-                os.environ["POLAR_SCL3_SS"] = str(ss); os.environ["POLAR_SCL3_CTAS"] = str(ctas)
+                dk.set_option("POLAR_SCL3_SS", int(str(ss))); dk.set_option("POLAR_SCL3_CTAS", int(str(ctas)))
                 try:
                     got = dk.scl_decode(x, tables, L, want_packed=True, want_info=False, want_pm=True, want_list=True)
                     torch.cuda.synchronize()

@@ -16,9 +16,9 @@ dev = torch.device("cuda", 0)
 fp = po.rm_frozen_pos(n, n - k)
 tables = dk.code_tables(fp, n, dev)
 _, _, x = dk.awgn_frontend(tables, B, po.ebnodb2no(3.0, 2, k / n), 1234)
-os.environ["POLAR_SCL_MODE"] = "1"
+dk.set_option("POLAR_SCL_MODE", int("1"))
 r2 = dk.scl_decode(x, tables, L, want_packed=True, want_info=False, want_pm=True, want_list=True)
-os.environ["POLAR_SCL_MODE"] = "2"
+dk.set_option("POLAR_SCL_MODE", int("2"))
 r3 = dk.scl_decode(x, tables, L, want_packed=True, want_info=False, want_pm=True, want_list=True)
 torch.cuda.synchronize()
 dl = (r3["list"] != r2["list"]).any(dim=2).any(dim=1)
