@@ -8,9 +8,15 @@ Workload (BASELINE.json configs[1]): SC decoder, k=512 n=1024 RM-rule code, AWGN
 batch B = 2^20 codewords per GPU (4 GiB of fp32 logits, larger than the 126 MB L2), synthetic, generated
 on the device by polar_awgn_frontend.  One step = one decode of the whole batch.
   value : decoded information Gbit/s, whole job (all ranks), inputs resident in HBM, CUDA-event timed.
-  e2e   : same metric through the host-buffer C-ABI call polar_sc_decode_host (pinned host logits ->
-          chunked H2D + decode + D2H of the packed decisions inside the timed region).
-  scl8  : the same two numbers for SCL L=8 + CRC11 (configs[2], B = 2^18), reported beside the headline.
+  e2e   : same metric through the reference's own boundary: SC_Dec.forward(cpu tensor [B,n]) -> cpu tensor [B,k] fp32
+          (polar_sc.py:113-133; page-locked input, chunked H2D + decode + D2H inside the timed region); the bit-packed
+          C-ABI side door (polar_sc_decode_host) and a pageable-input run are reported beside it.
+  scl8  : the same numbers for SCL L=8 + CRC11 (configs[2], B = 2^18).
+  link  : System_AWGN_model.forward (awgn_model.py:33-44) codewords/s: front end + decoder + API tensors.
+  sweep : the BLER sweep (sim.py:79-133 through sim_ber_device) for configs[3] (SCL-32 n=2048, 9 points, 2^16 codewords per
+          iteration over ALL ranks, target 1000 block errors, max 16 iterations) and for SC n=1024 (2^20 per iteration, 16
+          iterations per point), batch sharded over the ranks (strong scaling), 4 x int64 all-reduce per iteration inside
+          the timed region, with the per-iteration split.
 --impl reference: the CPU restatement of the reference (oracle/libpolar_oracle.so, all host threads) on a
 bounded sample per step (the reference itself is pure Python and cannot travel to the GPU box).
 """
@@ -192,6 +198,79 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------
+def source_stamp():
+    """sha1 over the kernel sources: ncu-derived constants (instructions per codeword, DRAM bytes per launch) are only
+    valid for the sources they were captured from (profiles/sc_counters.json carries the stamp of its capture)."""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(PKG, "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_counters(kernel_key):
+    """Counters captured by tools/refresh_counters.py for the CURRENT sources, else None (stale values are refused)."""
+    p = os.path.join(ROOT, "profiles", "sc_counters.json")
+    if not os.path.exists(p):
+        return None, "no capture"
+    d = json.load(open(p))
+    if d.get("source_stamp") != source_stamp():
+        return None, "stale: captured for sources %s, current %s" % (d.get("source_stamp"), source_stamp())
+    return d.get(kernel_key), "ncu capture of these sources (profiles/sc_counters.json)"
+
+
+def run_sweep(kind, world, dev, sampler, barrier, max_over_ranks):
+    """BLER sweep through the product's Monte-Carlo entry point (my_sn/sim.py::sim_ber_device; loop of sim.py:79-133,
+    caller main.py:55-59).  Strong scaling: the per-iteration batch is split over the ranks; every iteration all-reduces
+    the 4 counters (NCCL) in front of the on-device stop rules.  Timed wall clock, barrier + synchronize on both sides."""
+    import torch
+    from polar.enc import PolarEncoder
+    from polar.polar_sc import SC_Dec
+    from polar.polar_scl import SCL_Dec
+    from z_sys_model.awgn_model import System_AWGN_model
+    from my_sn.sim import sim_ber_device
+    rank = int(os.environ.get("RANK", "0"))
+    if kind == "scl32":
+        n, k, total_bs, mc, tgt, name = 2048, 1024, 1 << 16, 16, 1000, "SCL L=32 k=1024 n=2048 (configs[3])"
+        dec = lambda fp: SCL_Dec(fp, n, list_size=32)
+    else:
+        n, k, total_bs, mc, tgt, name = 1024, 512, 1 << 20, 16, None, "SC k=512 n=1024"
+        dec = lambda fp: SC_Dec(fp, n)
+    fp = frozen_set(n, k)
+    ebnos = np.arange(0.0, 4.5, 0.5)
+    bs = total_bs // world
+    mk = lambda: System_AWGN_model(n, k, PolarEncoder(fp, n, None), dec(fp), seed=1234 + rank)
+    sim_ber_device(mk(), ebnos[:2], bs, 2, target_block_errs=tgt, verbose=False)            # warm-up (allocators, NCCL)
+    out = None
+    times = []
+    for rep in range(2):
+        model = mk()
+        stats = {}
+        barrier()
+        w0 = time.perf_counter()
+        res = sim_ber_device(model, ebnos, bs, mc, target_block_errs=tgt, verbose=False, return_counters=True, stats=stats,
+                             profile=(rep == 1))
+        barrier()
+        w1 = time.perf_counter()
+        sampler.mark(w0, w1)
+        times.append(max_over_ranks((w1 - w0) * 1e3))
+        out = (res, stats)
+    res, stats = out
+    ms = min(times)
+    counters = res[2]
+    blocks = int(counters[:, 3].sum())                     # counted codewords over all ranks (the counters are all-reduced)
+    return {"workload": "%s BLER sweep Eb/N0 0:0.5:4 dB, %d codewords per iteration over all ranks, max_mc_iter %d, target_block_errs %s"
+                        % (name, total_bs, mc, tgt),
+            "api": "my_sn.sim.sim_ber_device(System_AWGN_model(...)) -- what sim_ber / PlotBER.simulate / main.py run",
+            "scaling": "strong", "n_gpus": world, "batch_per_rank": bs, "wall_ms": ms, "wall_ms_runs": times,
+            "simulated_codewords": blocks, "codewords_per_s": blocks / (ms * 1e-3), "info_gbit_per_s": blocks / (ms * 1e-3) * k / 1e9,
+            "iterations_counted": int(res[4].sum()), "iterations_queued": stats.get("queued"),
+            "bler": [float(v) for v in res[1]], "split_us_per_iteration": stats.get("split_us"),
+            "collective": "ncclAllReduce 4 x int64 per iteration" if world > 1 else "none (one rank)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -202,6 +281,8 @@ def main():
     ap.add_argument("--skip-scl", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-sweep", action="store_true")
+    ap.add_argument("--skip-link", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -211,6 +292,7 @@ def main():
     import torch.distributed as dist
     import d_kernels as dk
     from oracle import polar_oracle as po      # checker + cpu_baseline leg only
+    from polar.polar_sc import SC_Dec
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -263,7 +345,7 @@ def main():
 
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()                      # runs through the SC and the SCL timed regions (>= 0.5 s under load)
+        sampler.start()                      # runs through every timed region of this process
     for _ in range(args.warmup):
         sc_step()
     barrier()
@@ -284,6 +366,27 @@ def main():
     cws = world * B / (ms_per_step * 1e-3)
     value = cws * k / 1e9
 
+    # ---- same decode writing the reference's API tensor [B,k] fp32 as well ("report both") -----
+    u_api = torch.empty((B, k), dtype=torch.float32, device=dev)
+
+    def sc_api_step():
+        dk.check(lib.polar_sc_decode_f32(dk.ptr(logits), dk.ptr(tables.frozen_mask), n, B, None, dk.ptr(u_api), dk.ptr(tables.info_pos), k, stream))
+    sc_api_step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    api_steps = max(3, min(args.steps, 10))
+    a.record()
+    for _ in range(api_steps):
+        sc_api_step()
+    b.record()
+    barrier()
+    api_ms = max_over_ranks(a.elapsed_time(b) / api_steps)
+    api_tensor = {"value": world * B / (api_ms * 1e-3) * k / 1e9, "unit": "Gbit/s", "codewords_per_s": world * B / (api_ms * 1e-3),
+                  "ms_per_step": api_ms, "output": "[B,k] fp32 0./1. (what SC_Dec.forward returns; %d MiB per step) instead of the "
+                  "bit-packed decisions (%d MiB)" % (B * k * 4 >> 20, B * nw * 4 >> 20),
+                  "matches_packed": bool(torch.equal(u_api[:4096], dk.unpack_info(u_hat[:4096], tables.info_pos, n)))}
+    launches += api_steps + 1
+
     # ---- parity spot check in the same run (bit-exact vs the oracle on a slice; BLER sanity) ------------
     parity = None
     if rank == 0:
@@ -296,39 +399,89 @@ def main():
         dk.count_errors_packed(u_tx, u_hat, tables.info_mask, n, cnt)
         c = cnt.cpu().numpy()
         parity = {"bit_exact_vs_oracle": bool(np.array_equal(got, ref)), "checked_codewords": m_chk,
-                  "bler": float(c[1]) / B, "ber": float(c[0]) / (B * k)}
+                  "bler": float(c[1]) / B, "ber": float(c[0]) / (B * k),
+                  "full_batch_parity": "tests/test_gpu_fullsize.py (all 2^20 codewords, -m gpu)"}
 
-    # ---- end to end: pinned host logits -> polar_sc_decode_host (H2D + decode + D2H in the timed region)
+    # ---- end to end through the reference's boundary: SC_Dec.forward(cpu tensor) -> cpu tensor -----------
     e2e = None
     if not args.skip_e2e:
+        sc_mod = SC_Dec(fp, n, device=dev)
         h_logits = torch.empty((B, n), dtype=torch.float32, pin_memory=True)
         h_logits.copy_(logits)
+        ref_info = u_api[:4096].cpu()
+
+        def timed(fn, steps):
+            for _ in range(3):                                     # warm-up: staging buffers, and torch's page-locked
+                r = fn()                                           # allocator has to have BOTH result buffers it ping-pongs
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                r = fn()
+            torch.cuda.synchronize()
+            return max_over_ranks((time.perf_counter() - t0) * 1e3 / steps), r
+        e2e_steps = max(3, min(args.steps, 5))
+        w0 = time.perf_counter()
+        mod_ms, out = timed(lambda: sc_mod(h_logits), e2e_steps)
+        sampler.mark(w0, time.perf_counter())
+        ok = bool(out.device.type == "cpu" and out.shape == (B, k) and torch.equal(out[:4096], ref_info))
+        e2e = {"value": world * B / (mod_ms * 1e-3) * k / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": B * n * 4,
+               "d2h_bytes_per_step": B * k * 4, "ms_per_step": mod_ms, "codewords_per_s": world * B / (mod_ms * 1e-3),
+               "api": "SC_Dec.forward(cpu fp32 tensor [B,n], page-locked) -> cpu fp32 tensor [B,k] (x_run_sn_polar/polar/polar_sc.py; "
+                      "C ABI polar_sc_decode_host_f32: 128 MB chunks, H2D / decode / D2H on two streams)",
+               "matches_device_path": ok}
+        del out
+        # the bit-packed C-ABI side door (round 1's e2e number): 32x less D2H
         h_out = torch.empty((B, nw), dtype=torch.int32, pin_memory=True)
         mask_np = tables.mask_np
-
-        def e2e_step():
-            dk.check(lib.polar_sc_decode_host(h_logits.data_ptr(), mask_np.ctypes.data, n, B, h_out.data_ptr(), local))
-
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        e2e_steps = max(3, min(args.steps, 5))
-        for _ in range(e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
-        ok = bool(torch.equal(h_out[:4096], u_hat[:4096].cpu()))
-        e2e = {"value": world * B / (e2e_ms * 1e-3) * k / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": B * n * 4,
-               "d2h_bytes_per_step": B * nw * 4, "ms_per_step": e2e_ms, "codewords_per_s": world * B / (e2e_ms * 1e-3),
-               "api": "polar_sc_decode_host (pinned host buffers, 2-stream chunked copy/compute overlap)",
-               "matches_device_path": ok}
-        del h_logits, h_out
+        pk_ms, _ = timed(lambda: dk.check(lib.polar_sc_decode_host(h_logits.data_ptr(), mask_np.ctypes.data, n, B, h_out.data_ptr(), local)),
+                         e2e_steps)
+        e2e["packed_c_abi"] = {"value": world * B / (pk_ms * 1e-3) * k / 1e9, "unit": "Gbit/s", "ms_per_step": pk_ms,
+                               "d2h_bytes_per_step": B * nw * 4, "api": "polar_sc_decode_host (bit-packed decisions)",
+                               "matches_device_path": bool(torch.equal(h_out[:4096], u_hat[:4096].cpu()))}
+        del h_out
+        # pageable input (a plain torch CPU tensor): staged through page-locked buffers by host threads
+        Bp = min(B, 1 << 18)
+        pg = torch.empty((Bp, n), dtype=torch.float32)
+        pg.copy_(h_logits[:Bp])
+        pg_ms, outp = timed(lambda: sc_mod(pg), 3)
+        e2e["pageable_input"] = {"value": world * Bp / (pg_ms * 1e-3) * k / 1e9, "unit": "Gbit/s", "ms_per_step": pg_ms, "batch": Bp,
+                                 "api": "SC_Dec.forward(pageable cpu tensor)", "matches_device_path": bool(torch.equal(outp[:4096], ref_info))}
+        del h_logits, pg, outp
+    del u_api
 
     peaks, peak_src = measured_peaks()
+    # ---- link level: System_AWGN_model.forward (front end + decoder + API tensors), awgn_model.py:33-44 ----
+    link = None
+    if not args.skip_link:
+        from polar.enc import PolarEncoder
+        from z_sys_model.awgn_model import System_AWGN_model
+        Bl = 1 << 18
+        model = System_AWGN_model(n, k, PolarEncoder(fp, n, None), SC_Dec(fp, n, device=dev), device=dev, seed=77 + rank)
+        for _ in range(2):
+            model(Bl, EBNO_DB)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = dk.launch_count()
+        reps = 8
+        a.record()
+        for _ in range(reps):
+            bits, bits_hat = model(Bl, EBNO_DB)
+        b.record()
+        barrier()
+        launches += dk.launch_count() - l0
+        ms = max_over_ranks(a.elapsed_time(b) / reps)
+        link = {"metric": "link_model_throughput_sc_n1024", "codewords_per_s": world * Bl / (ms * 1e-3),
+                "value": world * Bl / (ms * 1e-3) * k / 1e9, "unit": "Gbit/s", "ms_per_step": ms, "batch": Bl,
+                "api": "System_AWGN_model.forward(batch_size, ebno_db) -> (bits [B,k], bits_hat [B,k]) fp32 device tensors "
+                       "(polar_awgn_frontend + sc4_kernel + 2 unpack kernels per call)",
+                "bler": float((bits != bits_hat).any(dim=1).float().mean().item())}
+        del bits, bits_hat, model
+
     # ---- SCL L=8 + CRC11 (configs[2]) ------------------------------------------------------------------
     scl = None
     if not args.skip_scl:
         from my_sn.fec.crc import CRCEncoder
+        from my_sn.fec.polar.dec import SCL_Dec as SclCrcDec
         Bs = SCL_BATCH
         crc_chk = CRCEncoder(SCL_CRC, k)                       # validity check spans all k decoder outputs (dec.py:508-516)
         crc = CRCEncoder(SCL_CRC, k - crc_chk.crc_length)      # generator for the payload
@@ -363,49 +516,66 @@ def main():
         launches += dk.launch_count() - l0
         scl_ms = max_over_ranks(a.elapsed_time(b) / scl_steps)
         scl_cws = world * Bs / (scl_ms * 1e-3)
-        tx = dk.pack_bits(bits)
         cnt = torch.zeros(2, dtype=torch.int64, device=dev)
-        txu = torch.zeros((Bs, nw), dtype=torch.int32, device=dev)
-        # transmitted u (info bits scattered): decode of a noiseless codeword is the cheapest way to get it packed
         full = torch.zeros((Bs, n), dtype=torch.float32, device=dev)
         full[:, tables.info_pos.long()] = bits
         txu = dk.pack_bits(full)
         dk.count_errors_packed(txu, best, tables.info_mask, n, cnt)
         c = cnt.cpu().numpy()
+        del full
+        sm_clk_now = 1965.0
+        cnts, cnts_src = ncu_counters("scl3_kernel<10,8>")
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        issue_peak = sms * 4 * sm_clk_now * 1e6
+        roof = {"bound": "issue", "unit": "warp-instr/s", "peak": issue_peak, "achieved": None, "frac": None, "traffic": None,
+                "counters": cnts_src,
+                "note": "the list decoder is instruction bound, not HBM bound (algorithmic bytes 4n + k/8 per codeword = %.4f of HBM "
+                        "peak at this rate): achieved = codewords/s x warp instructions per codeword (ncu smsp__inst_executed / batch), "
+                        "peak = SMs x 4 schedulers x SM clock" % (scl_cws / world * (4 * n + k / 8) / 1e9 / peaks["hbm_gbs"])}
+        if cnts:
+            ach = scl_cws / world * cnts["warp_instr_per_codeword"]
+            roof.update(achieved=ach, frac=ach / issue_peak, traffic=cnts.get("dram_bytes_per_launch"),
+                        warp_instr_per_codeword=cnts["warp_instr_per_codeword"])
         scl = {"metric": "decoded_info_throughput_scl8_crc11_n1024", "value": scl_cws * k / 1e9, "unit": "Gbit/s",
                "codewords_per_s": scl_cws, "ms_per_step": scl_ms, "batch": Bs, "ebno_db": SCL_EBNO_DB,
                "bler": float(c[1]) / Bs, "workload": "SCL L=8 k=512 (501+CRC11) n=1024 CRC-aided selection, batch 256K (configs[2])",
-               "kernel": "scl3_kernel<10,8,5,4,4> (polar_scl3.cu)",
-               "roofline": {"bound": "hbm", "achieved": scl_cws / world * (4 * n + k / 8) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                            "frac": scl_cws / world * (4 * n + k / 8) / 1e9 / peaks["hbm_gbs"], "traffic": None,
-                            "note": "algorithmic bytes (4n + k/8 per codeword) are irrelevant for the list decoder: 98 k warp "
-                                    "instructions per codeword (fp64 tree for 8 paths, literal log(1+exp) metric, rank of 16 "
-                                    "candidates per information bit); bound by per-warp latency at 58 % issue utilisation, "
-                                    "no pipe above 43 % (profiles/r01_scl3_kernel_ncu.md, DESIGN.md 4.2)"}}
+               "kernel": "scl3_kernel<10,8,...> (polar_scl3.cu)", "roofline": roof}
         if not args.skip_e2e:
+            mod = SclCrcDec(fp, n, SCL_L, crc_degree=SCL_CRC, cn_type="minsum", device=dev)
             h_lg = torch.empty((Bs, n), dtype=torch.float32, pin_memory=True)
             h_lg.copy_(lg)
-            h_best = torch.empty((Bs, nw), dtype=torch.int32, pin_memory=True)
-            rows_np = crc_chk.syndrome_rows(tables.info_pos_np, n)
-
-            def scl_e2e():
-                dk.check(lib.polar_scl_decode_host(h_lg.data_ptr(), tables.mask_np.ctypes.data, n, SCL_L, Bs, h_best.data_ptr(), None,
-                                                   rows_np.ctypes.data, crc.crc_length, local))
-            scl_e2e()
+            want = dk.unpack_info(best[:2048], tables.info_pos, n).cpu()
+            for _ in range(3):
+                out = mod(h_lg)
             barrier()
             t0 = time.perf_counter()
             for _ in range(3):
-                scl_e2e()
+                out = mod(h_lg)
             torch.cuda.synchronize()
             ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / 3)
             scl["e2e"] = {"value": world * Bs / (ms * 1e-3) * k / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": Bs * n * 4,
-                          "d2h_bytes_per_step": Bs * nw * 4, "ms_per_step": ms,
-                          "matches_device_path": bool(torch.equal(h_best[:2048], best[:2048].cpu()))}
+                          "d2h_bytes_per_step": Bs * k * 4 + Bs * SCL_L * 8, "ms_per_step": ms,
+                          "api": "my_sn.fec.polar.dec.SCL_Dec(crc_degree='CRC11').forward(cpu tensor) -> cpu tensor [B,k] fp32 "
+                                 "(polar_scl_decode_host_f32)",
+                          "matches_device_path": bool(torch.equal(out[:2048], want))}
+            del h_lg, out
         if rank == 0 and not args.skip_cpu:
             smp = 16384
             rate, thr, cnt_cw = cpu_oracle_rate("scl", lg[:smp].cpu().numpy(), po.frozen_vec(fp, n), SCL_L)
             scl["cpu_baseline"] = {"value": rate * k / 1e9, "unit": "Gbit/s", "codewords_per_s": rate, "cores": thr, "kind": "port",
                                    "sample": "first %d codewords of the GPU batch, C restatement (oracle/polar_oracle.c)" % cnt_cw}
+        del lg, cw, bits, payload, best, ws
+
+    # ---- BLER sweeps (strong scaling over the ranks) ---------------------------------------------------------
+    sweep = None
+    if not args.skip_sweep:
+        del logits, u_hat, u_tx
+        torch.cuda.empty_cache()
+        l0 = dk.launch_count()
+        sweep = {"scl32_n2048": run_sweep("scl32", world, dev, sampler, barrier, max_over_ranks),
+                 "sc_n1024": run_sweep("sc", world, dev, sampler, barrier, max_over_ranks)}
+        launches += dk.launch_count() - l0
+        logits = None
 
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
@@ -417,29 +587,29 @@ def main():
     cpu = None
     if not args.skip_cpu:
         smp = min(B, 1 << 20)
+        if logits is None:
+            _, _, logits = dk.awgn_frontend(tables, smp, no, 1234 + rank)
         rate, thr, cnt_cw = cpu_oracle_rate("sc", logits[:smp].cpu().numpy(), po.frozen_vec(fp, n))
         cpu = {"value": rate * k / 1e9, "unit": "Gbit/s", "codewords_per_s": rate, "cores": thr, "kind": "port",
                "sample": "first %d codewords of the GPU batch, C restatement of the reference (oracle/polar_oracle.c); "
                          "the Python reference itself measured 3270 cw/s on 8 vCPU (BASELINE.md)" % cnt_cw}
-    # the other two candidate bounds next to HBM.  Instruction counts are static (ncu, profiles/), rates live.
+    # the other candidate bounds next to HBM.  Instruction count / DRAM traffic come from an ncu capture of the
+    # CURRENT sources (profiles/sc_counters.json, stamped with a hash of csrc/); a stale capture is refused, not reused.
     sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     cw_rate_gpu = B / (kern_ms * 1e-3)
-    WARP_INSTR_PER_CW = 1515.5          # smsp__inst_executed.sum / 2^20 codewords (profiles/r01_sc4_kernel_ncu.md)
     issue_peak = sms * 4 * sm_clk * 1e6  # one warp instruction per scheduler and cycle
-    other_bounds = {
-        "issue": {"achieved": cw_rate_gpu * WARP_INSTR_PER_CW, "peak": issue_peak, "unit": "warp-instr/s",
-                  "frac": cw_rate_gpu * WARP_INSTR_PER_CW / issue_peak,
-                  "note": "%.1f warp instructions per codeword (ncu); serial SC chains, 2 warps per scheduler" % WARP_INSTR_PER_CW},
-        "dram_actual": {"achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
-                        "note": "filled from roofline.traffic below: bytes the kernel really moves / kernel time"}}
+    cnts, cnts_src = ncu_counters("sc4_kernel<10,2>")
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "sc_traffic_bytes_per_launch.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        if traffic and B == (1 << 20):
-            other_bounds["dram_actual"].update(achieved=traffic / (kern_ms * 1e-3) / 1e9,
-                                               frac=traffic / (kern_ms * 1e-3) / 1e9 / peaks["hbm_gbs"])
+    other_bounds = {"counters": cnts_src}
+    if cnts and B == (1 << 20):
+        traffic = cnts.get("dram_bytes_per_launch")
+        wi = cnts["warp_instr_per_codeword"]
+        other_bounds["issue"] = {"achieved": cw_rate_gpu * wi, "peak": issue_peak, "unit": "warp-instr/s",
+                                 "frac": cw_rate_gpu * wi / issue_peak, "warp_instr_per_codeword": wi}
+        if traffic:
+            other_bounds["dram_actual"] = {"achieved": traffic / (kern_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                           "frac": traffic / (kern_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
     line = {
         "metric": "decoded_info_throughput_sc_n1024", "value": value, "unit": "Gbit/s", "codewords_per_s": cws,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -453,11 +623,9 @@ def main():
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
                      "kernel": "sc4_kernel<10,2> (polar_sc4.cu)", "kernel_ms": kern_ms, "bytes_per_codeword": bytes_per_cw,
                      "other_bounds": other_bounds,
-                     "note": "algorithmic bytes = 4n + k/8 per codeword; stage m-1 is virtual: the channel row is read twice "
-                             "(once per half of the codeword), the two sibling passes in between read an L2-resident stage "
-                             "scratch instead, so DRAM traffic is ~2.0x the algorithmic bytes (profiles/; 2.9x before the "
-                             "scratch); binding bounds are the issue rate of the serial SC chains (128-leaf subtrees, 2 warps "
-                             "per scheduler) and DRAM bandwidth of the row passes (DESIGN.md 4.1)"},
+                     "note": "algorithmic bytes = 4n + k/8 per codeword; achieved = B x 4160 B / mean CUDA-event time of the kernel "
+                             "launches of the timed region (DESIGN.md 4.1)"},
+        "api_tensor_output": api_tensor, "link": link, "sweep": sweep,
         "cpu_baseline": cpu, "parity": parity, "scl8": scl,
     }
     print(json.dumps(line), flush=True)

@@ -48,27 +48,34 @@ PHD float f_minsum(float a, float b) {
 }
 PHD float f_minsum_noclip(float a, float b) { return f_minsum(a, b); }
 #else
-// The sign is taken from the product a*b (IEEE: sign(a*b) = sign(a) xor sign(b), also for zero, underflowed
-// and infinite products): FMUL issues on the FMA pipe, which this integer-heavy decoder leaves idle, instead
-// of a third ALU-pipe instruction.  (inf*0 = NaN only arises with magnitude 0, where the sign is unobservable.)
-PHD float f_minsum(float a, float b) {
-  float mag = fminf(fminf(fabsf(a), fabsf(b)), kLlrMax);
+// One instruction per min on sm_100a: `min.xorsign.abs.f32 d, a, b` = (sign(a) xor sign(b)) . min(|a|, |b|) (SASS
+// FMNMX.XORSIGN).  Clipping is the same instruction against +30 (positive: the sign stays a's), so f is two dependent
+// ALU-pipe instructions and the unclipped form ONE -- round 1 used FMNMX3 + FMUL (sign via the product) + LOP3.
 #if defined(__CUDA_ARCH__)
-  uint32_t sgn = f2u(__fmul_rn(a, b)) & 0x80000000u;
-#else
-  uint32_t sgn = (f2u(a) ^ f2u(b)) & 0x80000000u;
+PDEV float xorsign_min(float a, float b) {
+  float d;
+  asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
 #endif
+PHD float f_minsum(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return xorsign_min(xorsign_min(a, kLlrMax), b);
+#else
+  float mag = fminf(fminf(fabsf(a), fabsf(b)), kLlrMax);
+  uint32_t sgn = (f2u(a) ^ f2u(b)) & 0x80000000u;
   return u2f(f2u(mag) | sgn);
+#endif
 }
 // same, for inputs already known to lie in [-30, 30] (outputs of f): the clip is the identity.
 PHD float f_minsum_noclip(float a, float b) {
-  float mag = fminf(fabsf(a), fabsf(b));
 #if defined(__CUDA_ARCH__)
-  uint32_t sgn = f2u(__fmul_rn(a, b)) & 0x80000000u;
+  return xorsign_min(a, b);
 #else
+  float mag = fminf(fabsf(a), fabsf(b));
   uint32_t sgn = (f2u(a) ^ f2u(b)) & 0x80000000u;
-#endif
   return u2f(f2u(mag) | sgn);
+#endif
 }
 #endif
 // f on LOGITS (LLR = -logit, polar_sc.py:122): for min-sum the negation cancels exactly (sign.sign, |.|); the

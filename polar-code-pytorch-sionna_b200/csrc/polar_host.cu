@@ -202,8 +202,9 @@ using namespace polar;
 extern "C" int polar_sc_decode_host_f32(const float *h_logit, const uint32_t *h_frozen_mask, int n, int64_t B,
                                         uint32_t *h_u_packed, float *h_u_info_f32, const int32_t *h_info_pos, int k,
                                         int device) {
-  if (!h_logit || !h_frozen_mask || (!h_u_packed && !h_u_info_f32)) return set_error(POLAR_EINVAL, "sc host: null pointer");
   if (!is_pow2(n) || n < 2 || n > POLAR_MAX_N || B < 0) return set_error(POLAR_EINVAL, "sc host: bad n/B");
+  if (B == 0) return POLAR_OK;
+  if (!h_logit || !h_frozen_mask || (!h_u_packed && !h_u_info_f32)) return set_error(POLAR_EINVAL, "sc host: null pointer");
   if (h_u_info_f32 && (!h_info_pos || k < 1 || k > n)) return set_error(POLAR_EINVAL, "sc host: u_info requested without valid info_pos/k");
   if (device < 0 || device >= 64) return set_error(POLAR_EINVAL, "sc host: bad device");
   if (B == 0) return POLAR_OK;
@@ -221,15 +222,16 @@ extern "C" int polar_sc_decode_host_f32(const float *h_logit, const uint32_t *h_
 
 extern "C" int polar_sc_decode_host(const float *h_logit, const uint32_t *h_frozen_mask, int n, int64_t B,
                                     uint32_t *h_u_packed, int device) {
-  if (!h_u_packed) return set_error(POLAR_EINVAL, "sc host: null pointer");
+  if (B != 0 && !h_u_packed) return set_error(POLAR_EINVAL, "sc host: null pointer");
   return polar_sc_decode_host_f32(h_logit, h_frozen_mask, n, B, h_u_packed, nullptr, nullptr, 0, device);
 }
 
 extern "C" int polar_scl_decode_host_f32(const float *h_logit, const uint32_t *h_frozen_mask, int n, int L, int64_t B,
                                          uint32_t *h_best_packed, float *h_u_info_f32, const int32_t *h_info_pos, int k,
                                          double *h_pm_sorted, const uint32_t *h_crc_rows, int crc_len, int device) {
-  if (!h_logit || !h_frozen_mask || (!h_best_packed && !h_u_info_f32)) return set_error(POLAR_EINVAL, "scl host: null pointer");
   if (!is_pow2(n) || n < 2 || n > POLAR_SCL_MAX_N || !is_pow2(L) || L > POLAR_SCL_MAX_L || B < 0) return set_error(POLAR_EINVAL, "scl host: bad n/L/B");
+  if (B == 0) return POLAR_OK;
+  if (!h_logit || !h_frozen_mask || (!h_best_packed && !h_u_info_f32)) return set_error(POLAR_EINVAL, "scl host: null pointer");
   if (h_u_info_f32 && (!h_info_pos || k < 1 || k > n)) return set_error(POLAR_EINVAL, "scl host: u_info requested without valid info_pos/k");
   if (device < 0 || device >= 64) return set_error(POLAR_EINVAL, "scl host: bad device");
   if (B == 0) return POLAR_OK;
@@ -265,7 +267,7 @@ extern "C" int polar_scl_decode_host_f32(const float *h_logit, const uint32_t *h
 extern "C" int polar_scl_decode_host(const float *h_logit, const uint32_t *h_frozen_mask, int n, int L, int64_t B,
                                      uint32_t *h_best_packed, double *h_pm_sorted, const uint32_t *h_crc_rows,
                                      int crc_len, int device) {
-  if (!h_best_packed) return set_error(POLAR_EINVAL, "scl host: null pointer");
+  if (B != 0 && !h_best_packed) return set_error(POLAR_EINVAL, "scl host: null pointer");
   return polar_scl_decode_host_f32(h_logit, h_frozen_mask, n, L, B, h_best_packed, nullptr, nullptr, 0, h_pm_sorted, h_crc_rows,
                                    crc_len, device);
 }

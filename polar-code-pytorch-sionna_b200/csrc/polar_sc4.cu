@@ -633,10 +633,30 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
       }
     }
     if (u_info) {
-      for (int q = lane; q < nvalid * k; q += 32) {
-        const int c = q / k, t = q - c * k;
-        const int p = __ldg(info_pos + t);
-        u_info[(cw0 + c) * (int64_t)k + t] = (float)((beta[c * NWS + (p >> 5)] >> (p & 31)) & 1u);
+      // the API tensor [B, k] fp32 (polar_sc.py:127-133): a codeword's row at a time, one float4 per lane and round
+      // (bit -> 0.f / 1.f by masking the bit pattern of 1.0f: no int-to-float conversion on the slow pipe)
+      if ((k & 3) == 0 && (reinterpret_cast<uintptr_t>(u_info) & 15) == 0 && (reinterpret_cast<uintptr_t>(info_pos) & 15) == 0) {
+        const int k4 = k >> 2;
+        const int4 *ip = reinterpret_cast<const int4 *>(info_pos);
+        for (int c = 0; c < nvalid; ++c) {
+          float4 *row = reinterpret_cast<float4 *>(u_info + (cw0 + c) * (int64_t)k);
+          const uint32_t *bw = beta + c * NWS;
+          for (int t4 = lane; t4 < k4; t4 += 32) {
+            const int4 p = __ldg(ip + t4);
+            float4 o;
+            o.x = u2f((0u - ((bw[p.x >> 5] >> (p.x & 31)) & 1u)) & 0x3f800000u);
+            o.y = u2f((0u - ((bw[p.y >> 5] >> (p.y & 31)) & 1u)) & 0x3f800000u);
+            o.z = u2f((0u - ((bw[p.z >> 5] >> (p.z & 31)) & 1u)) & 0x3f800000u);
+            o.w = u2f((0u - ((bw[p.w >> 5] >> (p.w & 31)) & 1u)) & 0x3f800000u);
+            __stcs(row + t4, o);
+          }
+        }
+      } else {
+        for (int q = lane; q < nvalid * k; q += 32) {
+          const int c = q / k, t = q - c * k;
+          const int p = __ldg(info_pos + t);
+          u_info[(cw0 + c) * (int64_t)k + t] = (float)((beta[c * NWS + (p >> 5)] >> (p & 31)) & 1u);
+        }
       }
     }
     __syncwarp();
@@ -657,10 +677,14 @@ __global__ void nsmid_kernel(unsigned *out) {
   asm volatile("mov.u32 %0, %%nsmid;" : "=r"(v));
   *out = v;
 }
+#if !defined(POLAR_F_BOXPLUS)
 std::mutex g_scr_mu;
 std::atomic<float *> g_scr_buf[64];
+#endif
 
 }  // namespace
+
+#if !defined(POLAR_F_BOXPLUS)     // one scratch per device for the whole library: the boxplus unit uses ::polar's
 
 // Per-device stage scratch of the virtual-stage kernels (n >= 1024): %nsmid slots of kSc4ScratchPerSm (76 MB on a
 // 148-SM part) -- small enough to stay resident in the L2.  Allocated once by polar_init(device) (which may allocate and
@@ -689,6 +713,7 @@ float *sc4_scratch() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   return g_scr_buf[dev].load(std::memory_order_acquire);
 }
+#endif
 
 namespace {
 

@@ -64,11 +64,14 @@ class StopPredictor:
   from this point's known iterations, else a tenth of the previous point's (error rates fall with Eb/N0).  Either
   misprediction only costs time -- a discarded iteration or one host round trip -- never a different result."""
 
-  def __init__(self, target_bit_errs, target_block_errs, max_mc_iter, damp=0.1):
+  def __init__(self, target_bit_errs, target_block_errs, max_mc_iter, damp=0.1, first_point_prior=None):
     self.targets = (target_bit_errs, target_block_errs)
     self.max_iter = int(max_mc_iter)
     self.damp = damp
-    self.prev_rate = None            # (bit errors, block errors) per iteration of the previous point
+    # (bit errors, block errors) per iteration of the previous point; before the first point: the caller's prior (the
+    # device loop passes a block error rate of 1 and a bit error rate of 1/2 -- sweeps start at their lowest Eb/N0 --
+    # which `damp` turns into 0.1 / 0.05)
+    self.prev_rate = first_point_prior
     self.start_point()
 
   def start_point(self):
@@ -101,7 +104,7 @@ class StopPredictor:
 
 
 def sim_ber_device(model, ebno_dbs, batch_size, max_mc_iter, target_bit_errs=None, target_block_errs=None,
-                   early_stop=True, verbose=True, return_counters=False, lookahead=True, stats=None):
+                   early_stop=True, verbose=True, return_counters=False, lookahead=True, stats=None, profile=False):
   """the Monte-Carlo loop of sim.py:79-133 with every per-iteration step on the device.
 
   One iteration = front-end kernel (bits -> encoder -> QPSK -> AWGN -> logits; `model.device_frontend`) -> decoder kernel
@@ -113,7 +116,9 @@ def sim_ber_device(model, ebno_dbs, batch_size, max_mc_iter, target_bit_errs=Non
   kernel and its random numbers are handed to the next point, which makes the result identical to the host loop
   (`sim_ber(..., on_device=False)`) for the same seed.
   Returns (ber, bler) like sim_ber; with return_counters also the int64 [P,4] counters, status and iterations.
-  `stats` (dict, optional) receives {"queued": iterations launched, "counted": iterations counted}."""
+  `stats` (dict, optional) receives {"queued": iterations launched, "counted": iterations counted}; with `profile`
+  also "split_us": mean device time per iteration of front end / decoder / counter / all-reduce / control (CUDA events
+  on the launching stream at the stage boundaries) and the host wall time per iteration."""
   dist = _dist()
   rank0 = dist is None or dist.get_rank() == 0
   verbose = verbose and rank0
@@ -138,7 +143,9 @@ def sim_ber_device(model, ebno_dbs, batch_size, max_mc_iter, target_bit_errs=Non
                    "reached target bit errors", "reached target block errors"]
   fmt = "{: >9} |{: >11} |{: >11} |{: >12} |{: >12} |{: >13} |{: >12} |{: >12} |{: >10}"
   DEPTH = 2 if lookahead else 1
-  pred = StopPredictor(target_bit_errs, target_block_errs, max_mc_iter)
+  world = dist.get_world_size() if dist is not None else 1
+  pred = StopPredictor(target_bit_errs, target_block_errs, max_mc_iter,
+                       first_point_prior=(0.5 * B * tables.k * world, 1.0 * B * world))
   with tc.cuda.device(dev):
     nw = dk.words(model.n)
     u_tx = tc.empty((B, nw), dtype=tc.int32, device=dev)
@@ -150,16 +157,33 @@ def sim_ber_device(model, ebno_dbs, batch_size, max_mc_iter, target_bit_errs=Non
     host = [tc.zeros(8, dtype=tc.int64).pin_memory() for _ in range(DEPTH)]
     events = [tc.cuda.Event() for _ in range(DEPTH)]
 
+    marks = []                                               # profile: 6 timing events per queued iteration
+
+    def mark(row):
+      if profile:
+        e = tc.cuda.Event(enable_timing=True)
+        e.record()
+        row.append(e)
+
     def queue(i, ii, offset0):
+      row = []
+      mark(row)
       model.device_frontend(tables, B, ebno_dbs[i], model._seed, offset0 + ii * B, (u_tx, llr))
+      mark(row)
       dec.decode_packed(llr, tables, out=u_hat)
+      mark(row)
       delta.copy_(sizes)                                     # (0, 0, bits, blocks) of this rank's shard
       dk.count_errors_packed(u_tx, u_hat, tables.info_mask, model.n, delta)
+      mark(row)
       if dist is not None:
         dist.all_reduce(delta)                               # stream-ordered NCCL all-reduce of 4 x int64
+      mark(row)
       dk.mc_control(delta, state, target_bit_errs, target_block_errs, max_mc_iter)
       host[ii % DEPTH].copy_(state, non_blocking=True)
       events[ii % DEPTH].record()
+      mark(row)
+      if profile:
+        marks.append(row)
 
     for i in range(P):
       t0 = time.perf_counter()
@@ -204,6 +228,13 @@ def sim_ber_device(model, ebno_dbs, batch_size, max_mc_iter, target_bit_errs=Non
         break
   if stats is not None:
     stats.update(queued=int(n_queued), counted=int(iters.sum()), blocks=int(counters[:, 3].sum()))
+    if profile and marks:
+      tc.cuda.synchronize(dev)
+      names = ("front_end", "decode", "count", "all_reduce", "control")
+      split = {nm: float(np.mean([r[j].elapsed_time(r[j + 1]) for r in marks])) * 1e3 for j, nm in enumerate(names)}
+      split["device_total"] = float(np.mean([r[0].elapsed_time(r[5]) for r in marks])) * 1e3
+      split["host_wall"] = float(runtime.sum()) / max(len(marks), 1) * 1e6
+      stats["split_us"] = split
   with np.errstate(divide='ignore', invalid='ignore'):
     ber = np.nan_to_num(counters[:, 0] / counters[:, 2])
     bler = np.nan_to_num(counters[:, 1] / counters[:, 3])

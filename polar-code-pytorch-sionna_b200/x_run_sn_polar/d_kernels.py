@@ -283,6 +283,8 @@ def sc_decode_host(logits_cpu, tables, boxplus=False):
   x = _host_logits(logits_cpu, tables.n)
   B = x.shape[0]
   out = tc.empty((B, tables.k), dtype=tc.float32, pin_memory=B > 0)
+  if B == 0:
+    return out
   pos = tables.info_pos_np.astype(np.int32)
   check(lib().polar_sc_decode_host_f32(x.data_ptr(), tables.mask_np.ctypes.data, tables.n, B, None, out.data_ptr(),
                                        pos.ctypes.data, tables.k, init_device(tables.dev)))
@@ -295,6 +297,8 @@ def scl_decode_host(logits_cpu, tables, list_size, crc_rows_np=None, crc_len=0, 
   B, L = x.shape[0], int(list_size)
   out = tc.empty((B, tables.k), dtype=tc.float32, pin_memory=B > 0)
   pm = tc.empty((B, L), dtype=tc.float64, pin_memory=B > 0) if want_pm else None
+  if B == 0:
+    return out, pm
   pos = tables.info_pos_np.astype(np.int32)
   rows = None if crc_rows_np is None else np.ascontiguousarray(crc_rows_np, dtype=np.uint32)
   check(lib().polar_scl_decode_host_f32(x.data_ptr(), tables.mask_np.ctypes.data, tables.n, L, B, None, out.data_ptr(),
