@@ -498,7 +498,7 @@ def main():
         ws_ptr = (ws.data_ptr() + 255) // 256 * 256
 
         def scl_step():
-            dk.check(lib.polar_scl_decode(dk.ptr(lg), dk.ptr(tables.frozen_mask), n, SCL_L, Bs, dk.ptr(best), None, None, 0,
+            dk.check(lib.polar_scl_decode(dk.ptr(lg), dk.ptr(tables.frozen_mask), n, SCL_L, Bs, dk.ptr(best), None, None, k,
                                           None, None, dk.ptr(rows), crc.crc_length, ws_ptr, need, stream))
         scl_steps = max(3, min(args.steps, 5))
         for _ in range(2):
@@ -558,6 +558,13 @@ def main():
                           "api": "my_sn.fec.polar.dec.SCL_Dec(crc_degree='CRC11').forward(cpu tensor) -> cpu tensor [B,k] fp32 "
                                  "(polar_scl_decode_host_f32)",
                           "matches_device_path": bool(torch.equal(out[:2048], want))}
+            if not scl["e2e"]["matches_device_path"]:
+                full_want = dk.unpack_info(best, tables.info_pos, n).cpu()
+                badrows = (out != full_want).any(dim=1).nonzero().flatten()
+                dev_mod = mod(lg).cpu()
+                scl["e2e"]["debug"] = {"bad_rows": int(badrows.numel()), "first": badrows[:8].tolist(),
+                                       "device_module_equals_packed": bool(torch.equal(dev_mod, full_want)),
+                                       "host_equals_device_module": bool(torch.equal(dev_mod, out))}
             del h_lg, out
         if rank == 0 and not args.skip_cpu:
             smp = 16384

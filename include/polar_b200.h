@@ -94,7 +94,9 @@ int polar_sc_decode_boxplus_f32(const float *d_logit, const uint32_t *d_frozen_m
  *  d_list_packed  [B, L, POLAR_WORDS(n)] decisions of all L survivors, pm-ascending, or NULL
  *  d_crc_rows     [n] uint32: for info position i, the crc_len-bit syndrome contribution of that bit
  *                 (row of the reference's [k, crc_len] generator matrix, crc.py:54-74, MSB = parity
- *                 bit 0); 0 for frozen positions.  NULL / crc_len == 0: plain argmin.
+ *                 bit 0); 0 for frozen positions.  NULL / crc_len == 0: plain argmin.  With crc_len > 0, k must be
+ *                 the number of information positions (it scales the penalty 30 k of dec.py:517-518) even when
+ *                 d_u_info_f32 is NULL; k < 1 is rejected.
  *  d_workspace    polar_scl_workspace_bytes(n, L, B) bytes, 256-byte aligned. */
 size_t polar_scl_workspace_bytes(int n, int L, int64_t B);
 int polar_scl_decode(const float *d_logit, const uint32_t *d_frozen_mask, int n, int L, int64_t B,

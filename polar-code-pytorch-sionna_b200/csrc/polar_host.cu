@@ -259,7 +259,13 @@ extern "C" int polar_scl_decode_host_f32(const float *h_logit, const uint32_t *h
     POLAR_CUDA(cudaMemcpyAsync(C.crc, h_crc_rows, (size_t)n * 4, cudaMemcpyHostToDevice, C.st[0]));
   }
   POLAR_CUDA(cudaStreamSynchronize(C.st[0]));
-  HostJob J{h_logit, h_best_packed, h_u_info_f32, h_pm_sorted, n, h_u_info_f32 ? k : 0, L, B, true,
+  // k scales the CRC penalty (30 k, dec.py:517-518) even when no [B, k] tensor is requested: derive it from the mask then
+  int k_eff = k;
+  if (k_eff <= 0) {
+    k_eff = n;
+    for (int w = 0; w < POLAR_WORDS(n); ++w) k_eff -= __builtin_popcount(n < 32 ? (h_frozen_mask[w] & ((1u << n) - 1u)) : h_frozen_mask[w]);
+  }
+  HostJob J{h_logit, h_best_packed, h_u_info_f32, h_pm_sorted, n, k_eff, L, B, true,
             crc ? (const uint32_t *)C.crc : nullptr, crc ? crc_len : 0};
   return run_chunks(C, J, chunk, ws_need);
 }

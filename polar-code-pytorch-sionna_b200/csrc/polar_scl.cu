@@ -687,6 +687,7 @@ extern "C" int polar_scl_decode(const float *d_logit, const uint32_t *d_frozen_m
   if (!d_best_packed && !d_u_info_f32 && !d_pm_sorted && !d_list_packed) return set_error(POLAR_EINVAL, "scl: no output buffer");
   if (d_u_info_f32 && (!d_info_pos || k < 0 || k > n)) return set_error(POLAR_EINVAL, "scl: u_info requested without valid info_pos/k");
   if (crc_len < 0 || crc_len > 32 || (crc_len > 0 && !d_crc_rows)) return set_error(POLAR_EINVAL, "scl: bad crc_len / crc_rows");
+  if (crc_len > 0 && (k < 1 || k > n)) return set_error(POLAR_EINVAL, "scl: CRC-aided selection needs k (penalty 30 k, dec.py:517-518), got k=%d", k);
 #if !defined(POLAR_F_BOXPLUS)
   if (scl_mode() == 2 && scl3_supported(n, L) && ((uintptr_t)d_logit & 15) == 0) {
     Scl3Plan p3;

@@ -221,6 +221,56 @@ def test_host_buffer_entry_points_match_device_path(n, B, chunk_mb, monkeypatch)
     assert torch.equal(h_best, res["u_packed"].cpu()) and torch.equal(h_pm, res["pm"].cpu())
 
 
+@pytest.mark.parametrize("chunk_mb", [1, 128])
+def test_module_cpu_tensor_path_equals_device_path(chunk_mb):
+    """SC_Dec / SCL_Dec.forward on a CPU tensor go through polar_{sc,scl}_decode_host_f32 (chunked H2D /
+    decode / D2H on two streams, the [B,k] fp32 API tensor straight into page-locked host memory).  Same bits as the
+    device-tensor path for page-locked, pageable, non-contiguous and fp64 inputs; CRC-aided selection applies its 30 k
+    penalty on the host path too (the packed legacy entry point derives k from the mask)."""
+    torch, dk, po, co, dev = _env()
+    from polar.polar_sc import SC_Dec
+    from polar.polar_scl import SCL_Dec
+    from my_sn.fec.polar.dec import SCL_Dec as SclCrc
+    from my_sn.fec.crc import CRCEncoder
+    set_opt("POLAR_HOST_CHUNK_MB", chunk_mb)
+    n, k, B, L = 1024, 512, 3000, 8
+    fp = golden("frozen_sets")["rm_1024_512"]
+    tables = dk.code_tables(fp, n, dev)
+    chk = CRCEncoder("CRC11", k)
+    gen = CRCEncoder("CRC11", k - chk.crc_length)
+    payload = torch.randint(0, 2, (B, k - gen.crc_length), device=dev, dtype=torch.float32)
+    x = dk.qpsk_awgn_llr(dk.encode_f32(gen(payload), tables), po.ebnodb2no(3.0, 2, k / n), 5)
+    pinned = torch.empty((B, n), dtype=torch.float32, pin_memory=True); pinned.copy_(x)
+    pageable = x.cpu()
+    sc = SC_Dec(fp, n)
+    want = sc(x).cpu()
+    for inp in (pinned, pageable, pageable.double(), pageable.reshape(30, 100, n), torch.cat([pageable, pageable], 1)[:, n:]):
+        got = sc(inp)
+        assert got.device.type == "cpu" and got.dtype == torch.float32 and torch.equal(got.reshape(B, k), want)
+    scl = SCL_Dec(fp, n, L)
+    want = scl(x).cpu(); pm = scl.msg_pm.cpu()
+    assert torch.equal(scl(pageable), want) and torch.equal(scl.msg_pm, pm) and torch.equal(scl(pinned), want)
+    crc = SclCrc(fp, n, L, crc_degree="CRC11", cn_type="minsum")
+    want_crc = crc(x).cpu()
+    assert not torch.equal(want_crc, want)                       # the CRC picks another candidate on some codewords
+    assert torch.equal(crc(pinned), want_crc) and torch.equal(crc(pageable), want_crc)
+    # legacy packed entry point (no k argument): same selection as the device call that is told k
+    rows = chk.syndrome_rows(tables.info_pos_np, n)
+    h_best = torch.empty((B, n // 32), dtype=torch.int32, pin_memory=True)
+    dk.check(dk.lib().polar_scl_decode_host(pinned.data_ptr(), tables.mask_np.ctypes.data, n, L, B, h_best.data_ptr(), None,
+                                            rows.ctypes.data, chk.crc_length, 0))
+    assert torch.equal(dk.unpack_info(h_best.to(dev), tables.info_pos, n).cpu(), want_crc)
+    # the device C ABI refuses a CRC-aided call that does not say k (its penalty would silently be 0)
+    rows_d = torch.from_numpy(rows.view(np.int32).copy()).to(dev)
+    best = torch.empty((B, n // 32), dtype=torch.int32, device=dev)
+    need = int(dk.lib().polar_scl_workspace_bytes(n, L, B))
+    ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+    wp = (ws.data_ptr() + 255) // 256 * 256
+    rc = dk.lib().polar_scl_decode(dk.ptr(x), dk.ptr(tables.frozen_mask), n, L, B, dk.ptr(best), None, None, 0, None, None,
+                                   dk.ptr(rows_d), chk.crc_length, wp, need, dk.stream_ptr(dev))
+    assert rc == dk.POLAR_EINVAL
+
+
 def test_full_size_properties_sc():
     """BASELINE configs[1] size (n=1024, k=512, 2^20 codewords): size-independent properties.
     (a) noiseless codewords decode to the transmitted bits; (b) decisions do not depend on how the batch is
