@@ -70,7 +70,7 @@ int polar_init(int device) {
   POLAR_CUDA(cudaGetDevice(&prev));
   POLAR_CUDA(cudaSetDevice(device));
   query_device(device);
-  const int rc = sc4_scratch_init(device);
+  const int rc = sc_scratch_init(device);
   if (prev >= 0 && prev != device) cudaSetDevice(prev);
   return rc;
 }

@@ -7,13 +7,13 @@ namespace polar_bp { using namespace polar; }
 #define POLAR_F_BOXPLUS 1
 #define polar polar_bp
 #define polar_sc_decode_f32 polar_sc_decode_boxplus_f32
-#define polar_sc3_debug_read polar_sc3_bp_debug_read
 #define polar_sc4_debug_read polar_sc4_bp_debug_read
+#define polar_sc5_debug_read polar_sc5_bp_debug_read
 #define polar_scl_decode polar_scl_decode_boxplus
 #define polar_scl_workspace_bytes polar_scl_boxplus_workspace_bytes
 namespace polar {                // the launchers the units call across files, redeclared in the boxplus namespace
-int launch_sc3(const float *logit, const uint32_t *fmask, int n, int64_t B, uint32_t *u_packed, float *u_info,
-               const int32_t *info_pos, int k, int cw, int ctas, cudaStream_t st);
+int launch_sc5(const float *logit, const uint32_t *fmask, int n, int64_t B, uint32_t *u_packed, float *u_info,
+               const int32_t *info_pos, int k, int warps, cudaStream_t st);
 int launch_sc4(const float *logit, const uint32_t *fmask, int n, int64_t B, uint32_t *u_packed, float *u_info,
                const int32_t *info_pos, int k, int warps, cudaStream_t st);
 }

@@ -35,15 +35,17 @@ inline int opt_get(OptSlot &s, const char *name, int dflt) {
 }
 #define env_int(NAME, DFLT) ([&]() -> int { static ::polar::OptSlot s__; return ::polar::opt_get(s__, NAME, (DFLT)); }())
 
-// polar_sc4.cu: per-device stage scratch, allocated by polar_init()
-int sc4_scratch_init(int device);
-float *sc4_scratch();                                // nullptr until polar_init(device) ran
+// polar_sc5.cu: SC decoder with TMA-staged top stages and a scratch hierarchy (n in [1024, 8192])
+int launch_sc5(const float *logit, const uint32_t *fmask, int n, int64_t B, uint32_t *u_packed, float *u_info,
+               const int32_t *info_pos, int k, int warps, cudaStream_t st);
 
-// polar_sc3.cu: SC decoder with compile-time tree geometry (n in [128, 8192])
-int launch_sc3(const float *logit, const uint32_t *fmask, int n, int64_t B, uint32_t *u_packed, float *u_info,
-               const int32_t *info_pos, int k, int cw, int ctas, cudaStream_t st);
+// per-device stage scratch of the SC kernel for n >= 1024 (polar_sc5.cu), allocated by polar_init(): one slot per
+// physical SM; 4 MB hold the live nodes of stages 9 .. m-1 of every codeword in flight on the SM up to n = 8192
+constexpr size_t kScScratchPerSm = (size_t)4 << 20;
+int sc_scratch_init(int device);
+float *sc_scratch();                                 // nullptr until polar_init(device) ran
 
-// polar_sc4.cu: warp-autonomous SC decoder (n in [128, 2048])
+// polar_sc4.cu: warp-autonomous SC decoder, everything on chip (n in [128, 512])
 int launch_sc4(const float *logit, const uint32_t *fmask, int n, int64_t B, uint32_t *u_packed, float *u_info,
                const int32_t *info_pos, int k, int warps, cudaStream_t st);
 

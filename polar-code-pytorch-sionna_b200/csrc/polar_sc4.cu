@@ -1,4 +1,4 @@
-// polar_sc4.cu -- SC decoder, warp-autonomous mapping (default for 128 <= n <= 2048).
+// polar_sc4.cu -- SC decoder, warp-autonomous mapping for 128 <= n <= 512 (everything on chip; n >= 1024: polar_sc5.cu).
 //
 // Same algorithm and exact semantics as polar_sc.cu / polar_sc3.cu (x_run_sn_polar/polar/polar_sc.py:54-133,
 // SURVEY.md Appendix A).  Measurements of polar_sc3.cu (CTA per 32 codewords: one warp walks the 64-leaf
@@ -16,9 +16,6 @@
 //     storage); stages 7 and 6 plus the partial-sum words in shared memory (916 B per codeword).
 //   * only partial sums are produced on the serial path; the decisions are recovered once per codeword as
 //     u = T(x_hat).
-#include <atomic>
-#include <mutex>
-
 #include "polar_common.cuh"
 #include "polar_internal.h"
 
@@ -38,7 +35,6 @@ constexpr unsigned FULLMASK = 0xFFFFFFFFu;
     }                                                                                 \
   } while (0)
 
-constexpr size_t kSc4ScratchPerSm = (size_t)512 * 1024;   // 8 warps x 32 codewords x 512 floats (n=1024) = 4 x 32 x 1024 (n=2048)
 
 struct Sc4Layout {
   int nw, nws, n64, top, stride;
@@ -58,33 +54,6 @@ __host__ __device__ inline Sc4Layout sc4_layout(int m, int top, int bot, int war
 }
 
 PDEV float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
-// 128-bit read-only load with an L2 eviction policy (createpolicy) and no L1 allocation
-PDEV float4 ldg4_hint(const float *p, uint64_t policy) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy));
-  return v;
-}
-PDEV uint64_t l2_policy_evict_last() {
-  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
-}
-PDEV uint64_t l2_policy_evict_first() {
-  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
-}
-PDEV uint64_t l2_policy_evict_normal() {
-  uint64_t p; asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); return p;
-}
-// coherent 128-bit load / store with an L2 eviction policy (the stage scratch is written and read by the same kernel)
-PDEV float4 ldg4_coh_hint(const float *p, uint64_t policy) {
-  float4 v;
-  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy) : "memory");
-  return v;
-}
-PDEV void stg4_hint(float *p, const float4 v, uint64_t policy) {
-  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
-               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy) : "memory");
-}
 PDEV float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 PDEV void sts4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 PDEV float4 f4(const float4 a, const float4 b) {
@@ -194,134 +163,6 @@ __device__ __noinline__ void step_glob(const float *__restrict__ logit, int64_t 
   }
 }
 
-// channel (global, stage M) -> stage M-2 in TENSOR MEMORY through the virtual stage M-1.
-// kind = quarter of the codeword the target node covers: 0 LL, 1 LR, 2 RL, 3 RR (warp-uniform).
-// Work item p = lane + 32k = (codeword c, pair q): the float4 at elements 4q and 4q + H/2 of the stage M-2
-// node, i.e. exactly what one f/g of the next step consumes; it goes to TMEM columns 8k..8k+7 of the lane.
-// scr (optional): per-warp global scratch [32 codewords][N/2 floats] that stays in the L2.  The passes that compute a
-// LEFT stage M-2 node (kind 0 / 2) also store the stage M-1 node they had to form; the pass for its right sibling
-// (kind 1 / 3, a quarter of a decode later) then reads those N/2 values instead of the whole channel row again and
-// skips two of its three f/g per element.  scr_load is only set when the left pass of this batch really ran (it is
-// skipped when the left node is rate-0).
-template <int M, bool STORE>
-__device__ __noinline__ void step_virt_tmem(const int kind, const float *__restrict__ logit, int64_t cw0, int nvalid,
-                                            const uint32_t *beta, int nws, int lane, uint32_t tm_base, int hints,
-                                            float *scr) {
-  constexpr int N = 1 << M, H = N >> 2, PQ = H >> 3, HW = H >> 5;   // PQ pairs per codeword (multiple of 32)
-  constexpr int KMAX = PQ;                                          // 32 codewords * PQ pairs / 32 lanes
-  constexpr int VU = 2;                                             // pairs per round; rounds are double buffered
-  // The row is read four times, a quarter of the decode apart, and the rows in flight (148 SMs x 8 warps x 32 x 4 KB)
-  // exceed the L2.  hints = 1: keep every row until its last pass (evict_last x3, evict_first).  hints = 2: only protect
-  // the pairs of passes that are a quarter apart (0->1 and 2->3), halving the protected set so that it fits.
-  // With the stage scratch (STORE) the sibling pass does not come back to the row: stream it (evict_first) and leave
-  // the L2 to the scratch.
-  const uint64_t pol = STORE ? l2_policy_evict_first()
-                     : !hints ? l2_policy_evict_normal()
-                     : (hints == 2) ? ((kind & 1) ? l2_policy_evict_first() : l2_policy_evict_last())
-                                    : ((kind == 3) ? l2_policy_evict_first() : l2_policy_evict_last());
-  const bool right = kind >= 2, is_g = kind & 1;
-  const int gw = (kind == 3) ? 2 * HW : 0;
-  float4 c0[2][VU][2], c1[2][VU][2], c2[2][VU][2], c3[2][VU][2];      // [buffer][pair][element]
-  constexpr bool scr_store = STORE;
-  auto issue = [&](int buf, int k0) {
-#pragma unroll
-    for (int r = 0; r < VU; ++r) {
-      const int p = lane + 32 * (k0 + r);
-      const int c = (int)((unsigned)p / (unsigned)PQ), q = (int)((unsigned)p % (unsigned)PQ);
-      const int cl = c < nvalid ? c : nvalid - 1;
-      const float *row = logit + (cw0 + cl) * (int64_t)N + 4 * q;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const float *rp = row + e * (H / 2);
-        c0[buf][r][e] = ldg4_hint(rp, pol); c1[buf][r][e] = ldg4_hint(rp + H, pol);
-        c2[buf][r][e] = ldg4_hint(rp + 2 * H, pol); c3[buf][r][e] = ldg4_hint(rp + 3 * H, pol);
-      }
-    }
-  };
-  auto compute = [&](int buf, int k0) {
-#pragma unroll
-    for (int r = 0; r < VU; ++r) {
-      const int p = lane + 32 * (k0 + r);
-      const int c = (int)((unsigned)p / (unsigned)PQ), q = (int)((unsigned)p % (unsigned)PQ);
-      float4 o[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int j = 4 * q + e * (H / 2);
-        const uint32_t *bw = beta + c * nws + (j >> 5);
-        const int sh = j & 31;
-        float4 y0, y1;
-        if (!right) {              // left half of the codeword: stage M-1 node = f(channel)
-          y0 = f4neg(c0[buf][r][e], c2[buf][r][e]); y1 = f4neg(c1[buf][r][e], c3[buf][r][e]);
-        } else {                   // right half: stage M-1 node = g(channel, beta of the left half)
-          y0 = g4neg(c0[buf][r][e], c2[buf][r][e], bw[0] >> sh); y1 = g4neg(c1[buf][r][e], c3[buf][r][e], bw[HW] >> sh);
-        }
-        if constexpr (scr_store) {
-          float *sp = scr + c * (2 * H) + j;
-          const uint64_t pol_scr = l2_policy_evict_last();
-          stg4_hint(sp, y0, pol_scr); stg4_hint(sp + H, y1, pol_scr);
-        }
-        if (!is_g) o[e] = f4(y0, y1);
-        else o[e] = g4(y0, y1, bw[gw] >> sh);
-      }
-      tmem_st8(tm_base + 8 * (k0 + r), o[0], o[1]);
-    }
-  };
-  // software pipeline: the loads of round r+1 are in flight while round r is computed (static buffer indices)
-  issue(0, 0);
-#pragma unroll 1
-  for (int k0 = 0; k0 < KMAX; k0 += 2 * VU) {
-    issue(1, k0 + VU);
-    compute(0, k0);
-    if (k0 + 2 * VU < KMAX) issue(0, k0 + 2 * VU);
-    compute(1, k0 + VU);
-  }
-  tmem_wait_st();
-}
-
-// The right-sibling pass (kind 1 / 3) when the left pass of this batch stored the stage M-1 node: one g per element
-// from N/2 scratch values per codeword instead of three f/g from the whole channel row.
-template <int M>
-__device__ __noinline__ void step_virt_scr(const int kind, const uint32_t *beta, int nws, int lane, uint32_t tm_base,
-                                           const float *scr, const bool discard) {
-  constexpr int N = 1 << M, H = N >> 2, PQ = H >> 3, HW = H >> 5;
-  constexpr int KMAX = PQ, VU = 4;
-  const uint64_t pol = l2_policy_evict_last();
-  const int gw = (kind == 3) ? 2 * HW : 0;
-#pragma unroll 1
-  for (int k0 = 0; k0 < KMAX; k0 += VU) {
-    float4 a[VU][2], b[VU][2];
-#pragma unroll
-    for (int r = 0; r < VU; ++r) {
-      const int p = lane + 32 * (k0 + r);
-      const int c = (int)((unsigned)p / (unsigned)PQ), q = (int)((unsigned)p % (unsigned)PQ);
-      const float *sp = scr + c * (2 * H) + 4 * q;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) { a[r][e] = ldg4_coh_hint(sp + e * (H / 2), pol); b[r][e] = ldg4_coh_hint(sp + e * (H / 2) + H, pol); }
-    }
-#pragma unroll
-    for (int r = 0; r < VU; ++r) {
-      const int p = lane + 32 * (k0 + r);
-      const int c = (int)((unsigned)p / (unsigned)PQ), q = (int)((unsigned)p % (unsigned)PQ);
-      float4 o[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int j = 4 * q + e * (H / 2);
-        o[e] = g4(a[r][e], b[r][e], beta[c * nws + (j >> 5) + gw] >> (j & 31));
-      }
-      tmem_st8(tm_base + 8 * (k0 + r), o[0], o[1]);
-      if (discard && (lane & 7) == 0) {      // the 8 lanes of a 128-byte line have consumed it: drop it from the L2 unwritten
-        const float *sp = scr + c * (2 * H) + 4 * q;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          asm volatile("discard.global.L2 [%0], 128;" ::"l"(sp + e * (H / 2)) : "memory");
-          asm volatile("discard.global.L2 [%0], 128;" ::"l"(sp + e * (H / 2) + H) : "memory");
-        }
-      }
-    }
-  }
-  tmem_wait_st();
-}
-
 // channel (global, stage M) -> stage M-1 in TENSOR MEMORY (n = 512: no virtual stage needed).
 // Work item p = lane + 32k = (codeword c, pair q): the float4 at elements 4q and 4q + H/2 of the stage M-1 node.
 template <int M, bool IS_G>
@@ -383,15 +224,6 @@ PDEV void step_tmem(float *L, const uint32_t *beta, int stride, int nws, int lan
   }
 }
 
-// ask the L2 for the channel rows of the warp's next batch (one 4 KB bulk prefetch per lane and round)
-PDEV void prefetch_rows_l2(const float *base, size_t bytes, int lane) {
-  const char *p = reinterpret_cast<const char *>(base);
-  for (size_t off = (size_t)lane * 4096; off < bytes; off += (size_t)32 * 4096) {
-    const unsigned sz = (unsigned)((bytes - off) < 4096 ? (bytes - off) : 4096);
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + off), "r"(sz & ~15u) : "memory");
-  }
-}
-
 // ---- one lane per codeword: the 64-leaf subtree below the lane's stage-6 node (shared memory) -----
 PDEV uint2 bottom64(const float *node, uint32_t fm0, uint32_t fm1) {
   uint32_t bl = 0, bc = 0;
@@ -413,7 +245,6 @@ PDEV uint2 bottom64(const float *node, uint32_t fm0, uint32_t fm1) {
 }
 
 // MODE 0: stages 6..M-1 in shared memory (n <= 256).  MODE 1: stage M-1 in tensor memory (n = 512).
-// MODE 2: stage M-1 virtual, stage M-2 in tensor memory (n >= 1024).
 // the 128-leaf subtree below the lane's stage-7 node: both 64-leaf halves in registers (x[64] + the BetaTree levels),
 // so that shared memory only has to hold stage 7 (one more warp per SM) and stage 6 costs no LDS/STS round trip.
 PDEV uint64_t tree64(const float (&x)[64], uint64_t fm) {
@@ -453,11 +284,11 @@ PDEV uint4 bottom128(const float *node, uint64_t fm0, uint64_t fm1) {
 
 template <int M, int MODE>
 __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ logit, const uint32_t *__restrict__ fmask_g,
-                                                     int64_t B, int64_t nbatches, int l2_prefetch, int l2_hints, int dbg,
-                                                     float *scratch, int scr_discard, uint32_t *__restrict__ u_packed, float *__restrict__ u_info,
+                                                     int64_t B, int64_t nbatches, int dbg,
+                                                     uint32_t *__restrict__ u_packed, float *__restrict__ u_info,
                                                      const int32_t *__restrict__ info_pos, int k) {
-  constexpr bool TM = MODE >= 1, VIRT = MODE == 2;
-  constexpr int TS = VIRT ? M - 2 : M - 1;                  // stage held in tensor memory (TM only)
+  constexpr bool TM = MODE == 1;
+  constexpr int TS = M - 1;                                 // stage held in tensor memory (TM only)
   static_assert(MODE == 0 ? (M >= 7) : (TS >= 8 && TS <= 9), "sc4: the bottom stage must exist in shared memory; a warp reaches 512 TMEM columns");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int BOT = (M >= 8) ? 7 : 6;                      // stage of the node the per-lane subtree starts from
@@ -499,15 +330,6 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
     for (int idx = N64 - 1; idx >= 1; --idx) nz[idx] = nz[2 * idx] & nz[2 * idx + 1];
   __syncthreads();
 
-  // stage scratch of this warp: indexed by the PHYSICAL SM (only one CTA of this kernel fits on an SM, so concurrent
-  // launches on other streams can never share a slot), kSc4ScratchPerSm bytes per SM.  Recomputed at each use: the
-  // 128-leaf subtrees need every register, nothing extra may stay live across them.
-  auto scr_ptr = [&]() -> float * {
-    if (!VIRT || !scratch) return nullptr;
-    uint32_t smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    return scratch + (size_t)smid * (kSc4ScratchPerSm / 4) + (size_t)(threadIdx.x >> 5) * (32 * (N / 2));
-  };
   long long tlast = clock64();
   const long long tstart = tlast;
   const int64_t wstride = (int64_t)gridDim.x * nwarps;
@@ -519,29 +341,11 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
       // node entered at block i: the root, or the right child whose left sibling just finished
       const int S = (i == 0) ? M : BOT + (__ffs(i) - 1);
       int s = S;
-      if (VIRT && l2_prefetch && ((i + 1) & ((l2_prefetch == 2 ? N64 / 2 : N64 / 4) - 1)) == 0) {
-        // the block after this one starts with a pass over the channel rows (this batch's next quarter, or the next
-        // batch's first): ask the L2 for them now, one 64-leaf.. block (several microseconds) ahead of the loads
-        const int64_t pb = (i + 1 < N64) ? batch : batch + wstride;
-        if (pb < nbatches) {
-          const int64_t r = pb * 32 + lane;
-          if (r < B) {
-            const float *rp = logit + r * (int64_t)N;
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rp), "r"(N * 4) : "memory");
-          }
-        }
-      }
       bool zeroed = nz[(N64 >> (S - BOT)) + (i >> (S - BOT))] != 0;
-      if (!zeroed && S < M && !(VIRT && S == M - 1)) {
+      if (!zeroed && S < M) {
         // g step into (S, i) from its parent at stage S+1; the left sibling's beta starts at word 2*(i - 2^(S-6))
         const int left_word = WB * (i - (1 << (S - BOT)));
-        if (VIRT && S == M - 2) {
-          // the left sibling's pass stored its stage M-1 node unless it was skipped (left quarter rate-0)
-          const int kind = i < N64 / 2 ? 1 : 3;
-          float *scr = scr_ptr();
-          if (scr && !nz[4 + kind - 1]) step_virt_scr<M>(kind, beta, NWS, lane, tm_base, scr, scr_discard != 0);
-          else step_virt_tmem<M, false>(kind, logit, cw0, nvalid, beta, NWS, lane, tm_base, l2_hints, nullptr);
-        } else if (TM && !VIRT && S == M - 1) {
+        if (TM && S == M - 1) {
           step_glob_tmem<M, true>(logit, cw0, nvalid, beta, NWS, lane, tm_base);
         } else if (TM && S == TS - 1) {
           step_tmem<TS, true, BOT>(L, beta, stride, NWS, lane, tm_base, left_word);
@@ -551,18 +355,11 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
           step_smem_any<TOP - 1, true, BOT>(S, L, beta, stride, NWS, lane, left_word);
         }
         __syncwarp();
-        SC4_T((VIRT && S == M - 2) ? 0 : 1);
+        SC4_T(1);
       }
       while (!zeroed && s > BOT) {
         if (nz[(N64 >> (s - 1 - BOT)) + (i >> (s - 1 - BOT))]) { zeroed = true; --s; break; }   // left child is rate-0
-        if (VIRT && s == M) { --s; continue; }                                         // virtual stage: nothing stored
-        if (VIRT && s == M - 1) {
-          {
-            float *scr = scr_ptr();
-            if (scr) step_virt_tmem<M, true>(i < N64 / 2 ? 0 : 2, logit, cw0, nvalid, beta, NWS, lane, tm_base, l2_hints, scr);
-            else step_virt_tmem<M, false>(i < N64 / 2 ? 0 : 2, logit, cw0, nvalid, beta, NWS, lane, tm_base, l2_hints, nullptr);
-          }
-        } else if (TM && !VIRT && s == M) {
+        if (TM && s == M) {
           step_glob_tmem<M, false>(logit, cw0, nvalid, beta, NWS, lane, tm_base);
         } else if (TM && s == TS) {
           step_tmem<TS, false, BOT>(L, beta, stride, NWS, lane, tm_base, 0);
@@ -572,7 +369,7 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
           step_smem_any<TOP - 1, false, BOT>(s - 1, L, beta, stride, NWS, lane, 0);
         }
         __syncwarp();
-        SC4_T((VIRT && s == M - 1) ? 0 : 2);
+        SC4_T(2);
         --s;
       }
       const int lv0 = s - BOT;                   // the finished node covers 2^lv0 bottom blocks starting at i
@@ -672,48 +469,7 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
   }
 }
 
-__global__ void nsmid_kernel(unsigned *out) {
-  unsigned v;
-  asm volatile("mov.u32 %0, %%nsmid;" : "=r"(v));
-  *out = v;
-}
-#if !defined(POLAR_F_BOXPLUS)
-std::mutex g_scr_mu;
-std::atomic<float *> g_scr_buf[64];
-#endif
-
 }  // namespace
-
-#if !defined(POLAR_F_BOXPLUS)     // one scratch per device for the whole library: the boxplus unit uses ::polar's
-
-// Per-device stage scratch of the virtual-stage kernels (n >= 1024): %nsmid slots of kSc4ScratchPerSm (76 MB on a
-// 148-SM part) -- small enough to stay resident in the L2.  Allocated once by polar_init(device) (which may allocate and
-// synchronise; the decode entry points never do) and kept for the life of the process.
-int sc4_scratch_init(int device) {
-  if (device < 0 || device >= 64) return set_error(POLAR_EINVAL, "init: bad device %d", device);
-  std::lock_guard<std::mutex> lk(g_scr_mu);
-  if (g_scr_buf[device].load(std::memory_order_acquire)) return POLAR_OK;
-  unsigned *d_n = nullptr, h_n = 0;
-  POLAR_CUDA(cudaMalloc(&d_n, sizeof(unsigned)));
-  nsmid_kernel<<<1, 1>>>(d_n);
-  const cudaError_t e = cudaMemcpy(&h_n, d_n, sizeof(unsigned), cudaMemcpyDeviceToHost);
-  cudaFree(d_n);
-  if (e != cudaSuccess) return set_error(POLAR_ECUDA, "init: %s", cudaGetErrorString(e));
-  if (h_n == 0 || h_n > 1024) return set_error(POLAR_ECUDA, "init: implausible %%nsmid = %u", h_n);
-  void *p = nullptr;
-  if (cudaMalloc(&p, (size_t)h_n * kSc4ScratchPerSm) != cudaSuccess) {
-    (void)cudaGetLastError();
-    return set_error(POLAR_ENOMEM, "init: cudaMalloc of the %zu-byte SC stage scratch failed", (size_t)h_n * kSc4ScratchPerSm);
-  }
-  g_scr_buf[device].store((float *)p, std::memory_order_release);
-  return POLAR_OK;
-}
-float *sc4_scratch() {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  return g_scr_buf[dev].load(std::memory_order_acquire);
-}
-#endif
 
 namespace {
 
@@ -722,7 +478,7 @@ int launch_sc4_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t 
                  const int32_t *info_pos, int k, int warps, cudaStream_t st) {
   const int max_smem = device_max_smem_optin();
   constexpr bool TM = MODE >= 1;
-  constexpr int TS = MODE == 2 ? M - 2 : M - 1;
+  constexpr int TS = M - 1;
   int wmax = 8;
   if (TM) wmax = 4 * (512 >> TS);               // TMEM columns: 2^TS per warp, 512 per lane quarter
   if (wmax > 8) wmax = 8;
@@ -742,11 +498,7 @@ int launch_sc4_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t 
   int64_t grid = (nbatches + warps - 1) / warps;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
-  float *scratch = (MODE == 2 && env_int("POLAR_SC4_SCRATCH", 1)) ? sc4_scratch() : nullptr;
-  if (MODE == 2 && env_int("POLAR_SC4_SCRATCH", 1) && !scratch)
-    return set_error(POLAR_EINVAL, "sc: n=%d needs the per-device stage scratch -- call polar_init(device) once before decoding", 1 << M);
-  kern<<<(unsigned)grid, warps * 32, smem, st>>>(logit, fmask, B, nbatches, env_int("POLAR_SC4_PREFETCH", 0),
-                                                  env_int("POLAR_SC4_HINTS", 2), env_int("POLAR_SC3_DBG", 0), scratch, env_int("POLAR_SC4_DISCARD", 1), u_packed, u_info, info_pos, k);
+  kern<<<(unsigned)grid, warps * 32, smem, st>>>(logit, fmask, B, nbatches, env_int("POLAR_SC3_DBG", 0), u_packed, u_info, info_pos, k);
   count_launch();
   POLAR_CHECK_LAUNCH("sc4_kernel");
   return POLAR_OK;
@@ -754,15 +506,13 @@ int launch_sc4_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t 
 
 }  // namespace
 
-// n in [128, 2048].  warps = autonomous warps per SM (0 = as many as shared memory / tensor memory hold).
+// n in [128, 512].  warps = autonomous warps per SM (0 = as many as shared memory / tensor memory hold).
 int launch_sc4(const float *logit, const uint32_t *fmask, int n, int64_t B, uint32_t *u_packed, float *u_info,
                const int32_t *info_pos, int k, int warps, cudaStream_t st) {
   switch (ilog2(n)) {
     case 7: return launch_sc4_t<7, 0>(logit, fmask, B, u_packed, u_info, info_pos, k, warps, st);
     case 8: return launch_sc4_t<8, 0>(logit, fmask, B, u_packed, u_info, info_pos, k, warps, st);
     case 9: return launch_sc4_t<9, 1>(logit, fmask, B, u_packed, u_info, info_pos, k, warps, st);
-    case 10: return launch_sc4_t<10, 2>(logit, fmask, B, u_packed, u_info, info_pos, k, warps, st);
-    case 11: return launch_sc4_t<11, 2>(logit, fmask, B, u_packed, u_info, info_pos, k, warps, st);
     default: return set_error(POLAR_EINVAL, "sc4: n=%d not supported by this mapping", n);
   }
 }

@@ -6,18 +6,13 @@
 // sort the 2L candidates ascending, keep L.  Arithmetic is fp64 like the reference (numpy float64):
 // min-sum f with +-30 clip, g = (1-2u)a+b, exact softplus path metric.
 //
-// Mapping (DESIGN.md "SCL kernel"): ONE WARP PER CODEWORD, lane = path + L*sub (sub-lanes split the
-// elements of a node).  Nothing is ever copied when paths fork ("lazy copy"):
-//   * LLR stage s of path p lives in slot rowL[s] of a per-stage array laid out [element][slot];
-//     because all paths advance in lock-step, a stage is always *re*written by every path at the same
-//     time, so path p simply writes slot p and records rowL[s] = p; a fork only permutes the packed
-//     pointer rows (one 64-bit word per path: 5 bits per stage) with a warp shuffle.
-//   * Left-child partial sums are kept per stage the same way (rowB), stages below 32 bits travel by
-//     value in one 32-bit register (`small`).  Decisions u are recovered at the end from the root
-//     partial sums (the polar transform is an involution), so no per-path u array is forked either.
-//   * The 2L path-metric candidates are ranked with a warp bitonic network on (pm, index).
-// Stages >= s_glob of the LLR tree spill to a per-warp global workspace (L2 resident) when the list
-// is too large for shared memory (e.g. L=32, n=2048: 512 KB per codeword).
+// This file: the entry point polar_scl_decode and the GENERIC list kernel scl2_kernel<L> (lane = (codeword, path): a warp
+// decodes 32/L codewords, every lane walks all elements of its own path's nodes; nothing is copied on a fork -- a stage is
+// always rewritten by every path at the same time, so a path writes its own slot and a fork only permutes packed pointer
+// rows with a warp shuffle; decisions are recovered at the end from the root partial sums; the 2L candidates are ranked by
+// a bitonic network on (pm, index)).  It serves what the default mapping does not: n < 64 or n > 4096, L = 1, rows that
+// are not 16-byte aligned, and the exact-boxplus variant.  The default is polar_scl3.cu (virtual top stages, compile-time
+// tree, counting rank); both return identical bits (tests/test_gpu_parity.py).
 #include <math.h>
 
 #include "polar_internal.h"
@@ -59,268 +54,6 @@ struct SclParams {
   size_t smem_per_warp;
   int words_global;                                     // scl2: partial-sum words live in ws (after the LLR stages)
 };
-
-__host__ __device__ inline size_t scl_llr_smem_doubles(int L, int s_glob) { return (size_t)L * ((1u << s_glob) - 1u); }
-__host__ __device__ inline size_t scl_word_count(int L, int n) {   // bl stages 5..m-1 + root region
-  const int nw = n < 32 ? 1 : n >> 5;
-  return (size_t)L * (size_t)(2 * nw);
-}
-
-template <int L>
-__global__ void __launch_bounds__(128) scl_kernel(const SclParams P) {
-  constexpr int J = 32 / L;                                     // sub-lanes per path
-  constexpr int LOGL = (L == 1) ? 0 : (L == 2) ? 1 : (L == 4) ? 2 : (L == 8) ? 3 : (L == 16) ? 4 : 5;
-  constexpr unsigned FULL = 0xFFFFFFFFu;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int p = lane & (L - 1), j = lane >> LOGL;
-  const int n = P.n, m = P.m, nw = n < 32 ? 1 : n >> 5;
-  const int s_glob = P.s_glob;
-
-  unsigned char *base = smem_raw + (size_t)warp * P.smem_per_warp;
-  double *llr_s = reinterpret_cast<double *>(base);
-  uint32_t *bl = reinterpret_cast<uint32_t *>(llr_s + scl_llr_smem_doubles(L, s_glob));   // stage s>=5 at (2^(s-5)-1)*L
-  uint32_t *rootw = bl + (size_t)L * nw;                                                   // [nw][L]
-  const int64_t gwarp = (int64_t)blockIdx.x * nwarps + warp;
-  double *llr_g = P.ws ? P.ws + (size_t)gwarp * P.ws_doubles_per_warp : nullptr;
-  const size_t g_off = (size_t)L * ((1u << s_glob) - 1u);
-
-  auto stage_ptr = [&](int s) -> double * {   // array [2^s elements][L slots] of LLR stage s (< m)
-    const size_t off = (size_t)L * ((1u << s) - 1u);
-    return (s < s_glob) ? (llr_s + off) : (llr_g + (off - g_off));
-  };
-  const unsigned long long idrow = (unsigned long long)p * 0x0084210842108421ull;   // field s (5 bits) = p, s = 0..11
-
-  for (int64_t b = gwarp; b < P.B; b += (int64_t)gridDim.x * nwarps) {
-    const float *ch = P.logit + b * (int64_t)n;
-    double pm = (p == 0) ? 0.0 : kLlrMaxD;                       // polar_scl.py:192-194
-    unsigned long long rowL = idrow, rowB = idrow;
-    uint32_t small = 0u, rootreg = 0u, fword = 0u;
-
-    for (int i = 0; i < n; ++i) {
-      if ((i & 31) == 0) fword = __ldg(P.fmask + (i >> 5));
-      // ------------------------------------------------------------------ descent to leaf i
-      int t;
-      if (i == 0) {
-        t = m;
-      } else {
-        t = __ffs(i) - 1;
-        // g step: stage t+1 -> t, beta = left sibling's partial sums (polar_scl.py:140-144)
-        const int h = 1 << t;
-        double *dst = stage_ptr(t);
-        if (t + 1 == m) {
-          for (int e = j; e < h; e += J) {
-            unsigned u;
-            if (t < 5) u = (small >> ((1u << t) - 1u + e)) & 1u;
-            else u = (bl[((size_t)((1u << (t - 5)) - 1u) + (e >> 5)) * L + (unsigned)((rowB >> (5 * t)) & 31u)] >> (e & 31)) & 1u;
-            const double a = (double)(-__ldg(ch + e)), bb = (double)(-__ldg(ch + e + h));   // polar_scl.py:219,200
-            dst[(size_t)e * L + p] = g_minsum_d(a, bb, u);
-          }
-        } else {
-          const double *src = stage_ptr(t + 1);
-          const unsigned q = (unsigned)((rowL >> (5 * (t + 1))) & 31u);
-          for (int e = j; e < h; e += J) {
-            unsigned u;
-            if (t < 5) u = (small >> ((1u << t) - 1u + e)) & 1u;
-            else u = (bl[((size_t)((1u << (t - 5)) - 1u) + (e >> 5)) * L + (unsigned)((rowB >> (5 * t)) & 31u)] >> (e & 31)) & 1u;
-            dst[(size_t)e * L + p] = g_minsum_d(src[(size_t)e * L + q], src[(size_t)(e + h) * L + q], u);
-          }
-        }
-        __syncwarp();
-      }
-      // f steps: stage s -> s-1 along left children (polar_scl.py:134-137); inputs are this path's own slot
-      for (int s = (t < m ? t : m); s >= 1; --s) {
-        const int h = 1 << (s - 1);
-        double *dst = stage_ptr(s - 1);
-        if (s == m) {
-          for (int e = j; e < h; e += J)
-            dst[(size_t)e * L + p] = f_minsum_d((double)(-__ldg(ch + e)), (double)(-__ldg(ch + e + h)));
-        } else {
-          const double *src = stage_ptr(s);
-          for (int e = j; e < h; e += J)
-            dst[(size_t)e * L + p] = f_minsum_d(src[(size_t)e * L + p], src[(size_t)(e + h) * L + p]);
-        }
-        __syncwarp();
-      }
-      {  // stages 0..min(t, m-1) were rewritten by this path into its own slot
-        const int top = (t < m ? t : m - 1);
-        const unsigned long long msk = (top >= 11) ? 0x0FFFFFFFFFFFFFFFull : ((1ull << (5 * (top + 1))) - 1ull);
-        rowL = (rowL & ~msk) | (idrow & msk);
-      }
-      // ------------------------------------------------------------------ leaf
-      double x = stage_ptr(0)[p];
-      x = fmax(fmin(x, kLlrMaxD), -kLlrMaxD);                    // polar_scl.py:81
-      __syncwarp();   // every lane has read its leaf LLR before the next descent may overwrite stage 0
-      unsigned bit = 0u;
-      if ((fword >> (i & 31)) & 1u) {
-        pm += pm_penalty(x, 0u);                                   // frozen: u = 0
-      } else {
-        // fork: candidate e = u*L + p  (reference slot order [u=0 paths | u=1 paths], polar_scl.py:49-68)
-        if constexpr (L < 32) {
-          double key = (j < 2) ? pm + pm_penalty(x, (unsigned)j) : __longlong_as_double(0x7FF0000000000000ll);
-          int src = lane;
-#pragma unroll
-          for (int k = 2; k <= 2 * L; k <<= 1) {
-#pragma unroll
-            for (int d = k >> 1; d > 0; d >>= 1) {
-              const double pk = __shfl_xor_sync(FULL, key, d);
-              const int ps = __shfl_xor_sync(FULL, src, d);
-              const bool take_min = (((lane & d) == 0) == ((lane & k) == 0));
-              const bool partner_less = (pk < key) || (pk == key && ps < src);
-              if (take_min == partner_less) { key = pk; src = ps; }
-            }
-          }
-          const double nk = __shfl_sync(FULL, key, p);
-          const int ns = __shfl_sync(FULL, src, p);
-          const int parent = ns & (L - 1);
-          bit = (unsigned)(ns >> LOGL) & 1u;
-          pm = nk;
-          rowL = __shfl_sync(FULL, rowL, parent);
-          rowB = __shfl_sync(FULL, rowB, parent);
-          small = __shfl_sync(FULL, small, parent);
-        } else {
-          // L == 32: two candidates per lane, element index e = r*32 + lane  (r = u)
-          double k0 = pm + pm_penalty(x, 0u), k1 = pm + pm_penalty(x, 1u);
-          int s0 = lane, s1 = 32 + lane;
-#pragma unroll
-          for (int k = 2; k <= 64; k <<= 1) {
-#pragma unroll
-            for (int d = k >> 1; d > 0; d >>= 1) {
-              if (d == 32) {   // partner is the other register; block direction: ascending (e & 64 == 0)
-                const bool less10 = (k1 < k0) || (k1 == k0 && s1 < s0);
-                if (less10) { const double tk = k0; k0 = k1; k1 = tk; const int ts = s0; s0 = s1; s1 = ts; }
-              } else {
-                const double pk0 = __shfl_xor_sync(FULL, k0, d), pk1 = __shfl_xor_sync(FULL, k1, d);
-                const int ps0 = __shfl_xor_sync(FULL, s0, d), ps1 = __shfl_xor_sync(FULL, s1, d);
-                const bool lower = ((lane & d) == 0);
-                const bool up0 = (k == 64) ? true : (k == 32) ? true : ((lane & k) == 0);
-                const bool up1 = (k == 64) ? true : (k == 32) ? false : ((lane & k) == 0);
-                const bool less0 = (pk0 < k0) || (pk0 == k0 && ps0 < s0);
-                const bool less1 = (pk1 < k1) || (pk1 == k1 && ps1 < s1);
-                if ((lower == up0) == less0) { k0 = pk0; s0 = ps0; }
-                if ((lower == up1) == less1) { k1 = pk1; s1 = ps1; }
-              }
-            }
-          }
-          const int parent = s0 & 31;
-          bit = (unsigned)(s0 >> 5) & 1u;
-          pm = k0;
-          rowL = __shfl_sync(FULL, rowL, parent);
-          rowB = __shfl_sync(FULL, rowB, parent);
-          small = __shfl_sync(FULL, small, parent);
-        }
-      }
-      // ------------------------------------------------------------------ partial-sum cascade
-      // z = number of completed right children above leaf i  (polar_scl.py:147-153, [bl ^ br, br])
-      const int z = (i == n - 1) ? m : (__ffs(~i) - 1);
-      uint32_t cur = bit;
-      const int zs = z < 5 ? z : 5;
-      for (int s = 0; s < zs; ++s) {
-        const uint32_t w = 1u << s;
-        const uint32_t field = (small >> (w - 1u)) & ((1u << w) - 1u);
-        cur = (field ^ cur) | (cur << w);
-      }
-      if (z < 5) {
-        if (z < m) {
-          const uint32_t w = 1u << z, off = w - 1u, msk = ((1u << w) - 1u) << off;
-          small = (small & ~msk) | (cur << off);
-        } else {
-          rootreg = cur;                                           // n < 32: whole codeword
-        }
-      } else {
-        const int nwz = 1 << (z - 5);
-        uint32_t *dest = (z < m) ? (bl + (size_t)(nwz - 1) * L) : rootw;
-        if (j == 0) dest[(size_t)(nwz - 1) * L + p] = cur;
-        __syncwarp();
-        for (int s = 5; s < z; ++s) {
-          const int hw = 1 << (s - 5);
-          const uint32_t *bls = bl + (size_t)(hw - 1) * L;
-          const unsigned q = (unsigned)((rowB >> (5 * s)) & 31u);
-          for (int w = j; w < hw; w += J)
-            dest[(size_t)(nwz - 2 * hw + w) * L + p] = bls[(size_t)w * L + q] ^ dest[(size_t)(nwz - hw + w) * L + p];
-          __syncwarp();
-        }
-        if (z < m) rowB = (rowB & ~(31ull << (5 * z))) | ((unsigned long long)p << (5 * z));
-      }
-    }  // leaves
-
-    // ---------------------------------------------------------------------- epilogue
-    // root partial sums = codeword estimate x_hat; u_hat = T(x_hat) (involution)
-    if (m < 5) {
-      if (j == 0) rootw[p] = ptransform_rt(rootreg, m);
-      __syncwarp();
-    } else {
-      for (int w = j; w < nw; w += J) rootw[(size_t)w * L + p] = ptransform_rt(rootw[(size_t)w * L + p], 5);
-      __syncwarp();
-      for (int d = 1; d < nw; d <<= 1) {
-        for (int w = j; w < nw; w += J)
-          if (!(w & d)) rootw[(size_t)w * L + p] ^= rootw[(size_t)(w + d) * L + p];
-        __syncwarp();
-      }
-    }
-    // final sort by path metric (polar_scl.py:204)
-    double key = (j == 0) ? pm : __longlong_as_double(0x7FF0000000000000ll);
-    int src = lane;
-    if constexpr (L > 1) {
-#pragma unroll
-      for (int k = 2; k <= L; k <<= 1) {
-#pragma unroll
-        for (int d = k >> 1; d > 0; d >>= 1) {
-          const double pk = __shfl_xor_sync(FULL, key, d);
-          const int ps = __shfl_xor_sync(FULL, src, d);
-          const bool take_min = (((lane & d) == 0) == ((lane & k) == 0 || k == L));
-          const bool partner_less = (pk < key) || (pk == key && ps < src);
-          if (take_min == partner_less) { key = pk; src = ps; }
-        }
-      }
-    }
-    // lanes 0..L-1 now hold (pm ascending, source path)
-    if (P.pm_out && lane < L) P.pm_out[b * L + lane] = key;
-    if (P.list) {
-      for (int r = 0; r < L; ++r) {
-        const int sp = __shfl_sync(FULL, src, r) & (L - 1);
-        for (int w = lane; w < nw; w += 32) P.list[((size_t)b * L + r) * nw + w] = rootw[(size_t)w * L + sp];
-      }
-    }
-    // CRC-aided selection (my_sn/fec/polar/dec.py:507-520): pm += 30*k for candidates failing the CRC
-    double pen = key;
-    if (P.crc_len > 0 && P.crc_rows) {
-      for (int r = 0; r < L; ++r) {
-        const int sp = __shfl_sync(FULL, src, r) & (L - 1);
-        uint32_t syn = 0u;
-        for (int w = 0; w < nw; ++w) {
-          const uint32_t uw = rootw[(size_t)w * L + sp];
-          const int pos = w * 32 + lane;
-          if (pos < n && ((uw >> lane) & 1u)) syn ^= __ldg(P.crc_rows + pos);
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) syn ^= __shfl_xor_sync(FULL, syn, d);
-        if (lane == r && syn != 0u) pen = key + kLlrMaxD * (double)P.k;
-      }
-    }
-    // argmin over the L sorted candidates, first minimum wins (np.argmin, dec.py:520)
-    double bk = (lane < L) ? pen : __longlong_as_double(0x7FF0000000000000ll);
-    int bi = lane;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      const double ok = __shfl_xor_sync(FULL, bk, d);
-      const int oi = __shfl_xor_sync(FULL, bi, d);
-      if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
-    }
-    const int best_path = __shfl_sync(FULL, src, bi) & (L - 1);
-    if (P.best)
-      for (int w = lane; w < nw; w += 32) P.best[(size_t)b * nw + w] = rootw[(size_t)w * L + best_path];
-    if (P.u_info) {
-      float *row = P.u_info + b * (int64_t)P.k;
-      for (int tt = lane; tt < P.k; tt += 32) {
-        const int pos = __ldg(P.info_pos + tt);
-        row[tt] = (float)((rootw[(size_t)(pos >> 5) * L + best_path] >> (pos & 31)) & 1u);
-      }
-    }
-    __syncwarp();
-  }
-}
-
 
 // =====================================================================================================
 // scl2_kernel: lane = (codeword, path).  A warp decodes 32/L codewords at once, every lane owns one path of
@@ -580,13 +313,13 @@ __global__ void __launch_bounds__(128, SCL2_MINB) scl2_kernel(const SclParams P)
 
 struct SclPlan { int s_glob; size_t smem_per_warp; size_t ws_doubles_per_warp; int warps_per_cta; int64_t grid; int words_global = 0; };
 
-static int scl_mode() { return env_int("POLAR_SCL_MODE", 2); }   // 2: scl3 where supported, else 1 [default]; 1: lane = (codeword, path); 0: warp per codeword
+static int scl_mode() { return env_int("POLAR_SCL_MODE", 2); }   // 2: scl3 where supported, else scl2 [default]; 1: scl2 always (tests)
 
 static SclPlan scl_plan(int n, int L, int64_t B) {
   SclPlan pl;
   const int m = ilog2(n);
   const int max_smem = device_max_smem_optin();
-  if (scl_mode() >= 1) {
+  {
     const int nw = n < 32 ? 1 : n >> 5;
     const size_t words = (size_t)32 * 2 * nw * 4;
     const int budget = env_int("POLAR_SCL_SMEM_KB", 4) * 1024;    // per warp
@@ -616,38 +349,17 @@ static SclPlan scl_plan(int n, int L, int64_t B) {
     pl.grid = grid;
     return pl;
   }
-  const size_t words = scl_word_count(L, n) * 4;
-  const int budget = env_int("POLAR_SCL_SMEM_KB", 14) * 1024;     // per warp
-  int s_glob = m;
-  while (s_glob > 0 && scl_llr_smem_doubles(L, s_glob) * 8 + words > (size_t)budget) --s_glob;
-  pl.s_glob = s_glob;
-  pl.smem_per_warp = ((scl_llr_smem_doubles(L, s_glob) * 8 + words + 15) / 16) * 16;
-  pl.ws_doubles_per_warp = (s_glob < m) ? (size_t)L * ((1u << m) - (1u << s_glob)) : 0;
-  int wpc = env_int("POLAR_SCL_WARPS", 2);
-  if (wpc < 1) wpc = 1;
-  if (wpc > 4) wpc = 4;
-  while (wpc > 1 && pl.smem_per_warp * wpc > (size_t)max_smem) --wpc;
-  pl.warps_per_cta = wpc;
-  int ctas_per_sm = (int)((size_t)(228 * 1024) / (pl.smem_per_warp * wpc + 1024));
-  if (ctas_per_sm < 1) ctas_per_sm = 1;
-  if (ctas_per_sm > 32) ctas_per_sm = 32;
-  int64_t grid = (B + wpc - 1) / wpc;
-  const int64_t cap = (int64_t)device_sm_count() * ctas_per_sm;
-  if (grid > cap) grid = cap;
-  if (grid < 1) grid = 1;
-  pl.grid = grid;
-  return pl;
 }
 
 template <int L>
 static int launch_scl(SclParams &P, const SclPlan &pl, cudaStream_t st) {
-  void (*kern)(const SclParams) = (scl_mode() >= 1) ? scl2_kernel<L> : scl_kernel<L>;
+  void (*kern)(const SclParams) = scl2_kernel<L>;
   const size_t smem = pl.smem_per_warp * pl.warps_per_cta;
   if (smem > (size_t)device_max_smem_optin()) return set_error(POLAR_ENOMEM, "scl: needs %zu B shared memory per CTA", smem);
   POLAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)pl.grid, pl.warps_per_cta * 32, smem, st>>>(P);
   count_launch();
-  POLAR_CHECK_LAUNCH("scl_kernel");
+  POLAR_CHECK_LAUNCH("scl2_kernel");
   return POLAR_OK;
 }
 

@@ -47,71 +47,16 @@ def test_sc_matches_oracle_random(n, k, B, ebno):
     assert np.array_equal(u_info.cpu().numpy().astype(np.uint8), ref[:, po.info_positions(fp, n)])
 
 
-@pytest.mark.parametrize("cw", [1, 2, 4, 8, 16, 32])
-def test_sc_all_codewords_per_warp_variants(cw, monkeypatch):
-    import torch
-    from oracle import polar_oracle as po, c_oracle as co
-    dk = _dk()
-    n, k, B = 256, 128, 1111
-    set_opt("POLAR_SC_MODE", "0")           # warp-per-CW-codewords mapping
-    set_opt("POLAR_SC_CW", str(cw))
-    fp = po.rm_frozen_pos(n, n - k)
-    _, logits = awgn_logits(np.random.default_rng(cw), n, k, fp, B, 2.0)
-    ref = co.sc_decode_full(logits, po.frozen_vec(fp, n))
-    tables = dk.code_tables(fp, n, torch.device("cuda", 0))
-    _, u_packed = dk.sc_decode(torch.from_numpy(logits).cuda(), tables, want_info=False, want_packed=True)
-    assert np.array_equal(unpack_words(u_packed.cpu().numpy(), n), ref)
-
-
-@pytest.mark.parametrize("ctas,threads,n", [(1, 32, 256), (2, 128, 1024), (3, 64, 512), (4, 256, 1024), (8, 128, 2048), (16, 96, 64)])
-def test_sc_cta_mapping_variants(ctas, threads, n, monkeypatch):
-    import torch
-    from oracle import polar_oracle as po, c_oracle as co
-    dk = _dk()
-    k, B = n // 2, 3001
-    set_opt("POLAR_SC_MODE", "1")           # CTA-cooperative mapping (default)
-    set_opt("POLAR_SC_CTAS", str(ctas))
-    set_opt("POLAR_SC_THREADS", str(threads))
-    fp = po.rm_frozen_pos(n, n - k)
-    _, logits = awgn_logits(np.random.default_rng(ctas), n, k, fp, B, 3.0)
-    logits[::9] = np.round(logits[::9])
-    ref = co.sc_decode_full(logits, po.frozen_vec(fp, n))
-    tables = dk.code_tables(fp, n, torch.device("cuda", 0))
-    u_info, u_packed = dk.sc_decode(torch.from_numpy(logits).cuda(), tables, want_info=True, want_packed=True)
-    assert np.array_equal(unpack_words(u_packed.cpu().numpy(), n), ref)
-    assert np.array_equal(u_info.cpu().numpy().astype(np.uint8), ref[:, po.info_positions(fp, n)])
-
-
-@pytest.mark.parametrize("cw,ctas,n", [(32, 0, 128), (32, 0, 256), (7, 2, 512), (32, 0, 1024), (26, 4, 1024), (1, 1, 1024),
-                                       (5, 0, 1024), (32, 0, 2048), (16, 0, 4096), (32, 0, 8192)])
-def test_sc3_mapping_variants(cw, ctas, n, monkeypatch):
-    """polar_sc3.cu (default mapping): virtual top stage for n >= 1024, 64-leaf register subtrees."""
-    import torch
-    from oracle import polar_oracle as po, c_oracle as co
-    dk = _dk()
-    k, B = n // 2, 2000 if n <= 2048 else 300
-    set_opt("POLAR_SC_MODE", "2")
-    set_opt("POLAR_SC_CTA_CW", str(cw))
-    set_opt("POLAR_SC_CTAS", str(ctas))
-    fp = po.rm_frozen_pos(n, n - k)
-    _, logits = awgn_logits(np.random.default_rng(cw + n), n, k, fp, B, 3.0)
-    logits[::9] = np.round(logits[::9])
-    ref = co.sc_decode_full(logits, po.frozen_vec(fp, n))
-    tables = dk.code_tables(fp, n, torch.device("cuda", 0))
-    u_info, u_packed = dk.sc_decode(torch.from_numpy(logits).cuda(), tables, want_info=True, want_packed=True)
-    assert np.array_equal(unpack_words(u_packed.cpu().numpy(), n), ref)
-    assert np.array_equal(u_info.cpu().numpy().astype(np.uint8), ref[:, po.info_positions(fp, n)])
-
-
-@pytest.mark.parametrize("warps,n,B", [(0, 128, 5000), (3, 256, 3001), (0, 512, 2000), (0, 1024, 9000), (1, 1024, 100),
-                                       (5, 1024, 4097), (7, 1024, 31), (0, 2048, 1500), (2, 2048, 700)])
-def test_sc4_warp_autonomous_variants(warps, n, B, monkeypatch):
-    """polar_sc4.cu (default mapping): a warp per 32 codewords, tensor-memory scratch for n >= 1024."""
+@pytest.mark.parametrize("warps,n,B", [(0, 64, 3000), (0, 128, 5000), (3, 256, 3001), (0, 512, 2000), (0, 1024, 9000), (1, 1024, 100),
+                                       (5, 1024, 4097), (7, 1024, 31), (0, 2048, 1500), (2, 2048, 700), (0, 4096, 1100),
+                                       (3, 4096, 333), (0, 8192, 500), (1, 8192, 65)])
+def test_sc_warp_autonomous_variants(warps, n, B, monkeypatch):
+    """polar_sc4.cu (n <= 512) / polar_sc5.cu (n >= 1024): a warp per 32 codewords; any number of warps per SM (the
+    staging ring of sc5 is shared by the warps of a CTA), ragged batches."""
     import torch
     from oracle import polar_oracle as po, c_oracle as co
     dk = _dk()
     k = n // 2
-    set_opt("POLAR_SC_MODE", "3")
     set_opt("POLAR_SC_WARPS_SM", str(warps))
     fp = po.rm_frozen_pos(n, n - k)
     _, logits = awgn_logits(np.random.default_rng(warps + n), n, k, fp, B, 3.0)
@@ -123,14 +68,13 @@ def test_sc4_warp_autonomous_variants(warps, n, B, monkeypatch):
     assert np.array_equal(u_info.cpu().numpy().astype(np.uint8), ref[:, po.info_positions(fp, n)])
 
 
-@pytest.mark.parametrize("mode", [2, 3])
-@pytest.mark.parametrize("n", [128, 1024, 2048])
-def test_sc3_extreme_frozen_patterns(n, mode, monkeypatch):
-    """rate-0 halves / quarters (virtual-stage corner cases), none frozen, single info bit, alternating, 5G-like."""
+@pytest.mark.parametrize("n", [64, 128, 512, 1024, 2048, 4096])
+def test_sc_extreme_frozen_patterns_all_mappings(n):
+    """rate-0 halves / quarters / 128-leaf blocks (descent and skip corner cases), none frozen, single info bit,
+    alternating, 5G-like."""
     import torch
     from oracle import polar_oracle as po, c_oracle as co
     dk = _dk()
-    set_opt("POLAR_SC_MODE", str(mode))
     B = 333
     rng = np.random.default_rng(n)
     logits = (rng.standard_normal((B, n)) * 4).astype(np.float32)
@@ -138,7 +82,8 @@ def test_sc3_extreme_frozen_patterns(n, mode, monkeypatch):
     pats = [np.arange(n), np.arange(0), np.arange(n - 1), np.arange(0, n, 2), np.arange(n // 2), np.arange(n // 2, n),
             np.arange(n // 4), np.arange(3 * n // 4), np.concatenate([np.arange(n // 4), np.arange(n // 2, 3 * n // 4)]),
             np.concatenate([np.arange(64), np.arange(128, 128 + 64)]) % n, np.arange(n // 4, n),
-            np.sort(rng.choice(n, n // 3, replace=False))]
+            np.sort(rng.choice(n, n // 3, replace=False)),
+            np.arange(256, 512) % n, np.arange(128, 256) % n, np.arange(0, 128) % n, np.arange(n // 2 - 128, n // 2 + 384) % n]
     for fp in pats:
         fp = np.unique(fp)
         ref = co.sc_decode_full(logits, po.frozen_vec(fp, n))
@@ -147,25 +92,26 @@ def test_sc3_extreme_frozen_patterns(n, mode, monkeypatch):
         assert np.array_equal(unpack_words(u_packed.cpu().numpy(), n), ref), len(fp)
 
 
-@pytest.mark.parametrize("n,B", [(1024, 1 << 18), (2048, 1 << 16)])
-def test_sc_stage_scratch_is_transparent(n, B, monkeypatch):
-    """polar_sc4.cu keeps the stage m-1 node of every codeword in flight in an L2-resident scratch indexed by the physical
-    SM.  A full-GPU batch (every SM, every warp slot, many batches per warp) must give the same bits with and without
-    it, also when two streams decode different batches at the same time (slots are per SM, never per launch)."""
+@pytest.mark.parametrize("n,B", [(1024, 1 << 18), (2048, 1 << 16), (4096, 1 << 14)])
+def test_sc_stage_scratch_is_per_sm_and_stream_safe(n, B):
+    """polar_sc5.cu keeps the live nodes of stages 9 .. m-1 of every codeword in flight in a global scratch indexed by the
+    PHYSICAL SM.  A full-GPU batch (every SM, every warp slot, many batches per warp) must be deterministic, independent of
+    how the batch is split, and unchanged when two streams decode different batches at the same time (slots are per SM,
+    never per launch); a 4096-codeword slice is checked against the C restatement."""
     import torch
-    from oracle import polar_oracle as po
+    from oracle import polar_oracle as po, c_oracle as co
     dk = _dk()
     k = n // 2
     dev = torch.device("cuda", 0)
     fp = po.rm_frozen_pos(n, n - k)
     tables = dk.code_tables(fp, n, dev)
     _, _, x = dk.awgn_frontend(tables, B, po.ebnodb2no(3.0, 2, k / n), 31337)
-    set_opt("POLAR_SC4_SCRATCH", "0")
     _, ref = dk.sc_decode(x, tables, want_info=False, want_packed=True)
     torch.cuda.synchronize()
-    set_opt("POLAR_SC4_SCRATCH", "1")
     _, got = dk.sc_decode(x, tables, want_info=False, want_packed=True)
     assert torch.equal(got, ref)
+    want = co.sc_decode_full(x[:4096].cpu().numpy(), po.frozen_vec(fp, n))
+    assert np.array_equal(unpack_words(ref[:4096].cpu().numpy(), n), want)
     # two streams, small launches that do not fill the GPU -> the two kernels really overlap
     h = B // 64
     outs = [torch.empty((h, n // 32), dtype=torch.int32, device=dev) for _ in range(8)]
