@@ -65,7 +65,7 @@ float *sc_scratch() {
 #endif
 
 // phase timeline of warp 0 of CTA 0 (cycles), filled only when POLAR_SC3_DBG=1 (tools/perf_probe.py):
-// 0 descents, 1 g steps (tmem), 2 f steps (tmem), 3 128-leaf subtrees, 4 merges, 5 outputs, 6 total, 7 batches
+// 0 descents from the channel, 1 descents from the scratch, 2 tensor-memory steps, 3 128-leaf subtrees, 4 merges, 5 outputs, 6 total, 7 batches
 __device__ unsigned long long g_sc5_dbg[8];
 
 namespace {
@@ -458,22 +458,40 @@ __device__ __noinline__ void descent(const float *__restrict__ src, const int nv
 template <bool IS_G>
 PDEV void step_tmem(float *L, const uint32_t *beta, const int stride, const int nws, const int lane, const uint32_t tm_base,
                     const int left_word) {
-  constexpr int PQ = 32;                            // 128 outputs per codeword = 32 float4
-#pragma unroll 2
-  for (int k0 = 0; k0 < PQ; k0 += 2) {
-    Tm8 v0, v1;
+  // 128 outputs per codeword = 32 float4; round k = codeword k, lane = float4 column.  tcgen05.wait::ld waits for every
+  // load issued before it, so the loads of group g+1 are issued right AFTER the wait for group g and fly while group g
+  // is computed (two register sets of 4 x 8).
+  const int j = lane << 2;
+  const uint32_t *bp = beta + left_word + (j >> 5);
+  const int sh = j & 31;
+  float *dst = L + j;
+  Tm8 a0, a1, a2, a3, b0, b1, b2, b3;
+  auto issue4 = [&](const int k0, Tm8 &v0, Tm8 &v1, Tm8 &v2, Tm8 &v3) {
     tmem_ld8_issue(tm_base + 8 * k0, v0);
     tmem_ld8_issue(tm_base + 8 * (k0 + 1), v1);
-    tmem_ld_wait(v0, v1);
+    tmem_ld8_issue(tm_base + 8 * (k0 + 2), v2);
+    tmem_ld8_issue(tm_base + 8 * (k0 + 3), v3);
+  };
+  auto compute4 = [&](const int k0, const Tm8 &v0, const Tm8 &v1, const Tm8 &v2, const Tm8 &v3) {
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int c = k0 + r, j = lane << 2;          // round k = codeword k, lane = float4 column
-      const float4 a = tm_lo(r ? v1 : v0), b = tm_hi(r ? v1 : v0);
+    for (int r = 0; r < 4; ++r) {
+      const Tm8 &v = r == 0 ? v0 : r == 1 ? v1 : r == 2 ? v2 : v3;
+      const float4 a = tm_lo(v), b = tm_hi(v);
       float4 o;
-      if (IS_G) o = g4(a, b, beta[c * nws + left_word + (j >> 5)] >> (j & 31));
+      if (IS_G) o = g4(a, b, bp[(k0 + r) * nws] >> sh);
       else o = f4(a, b);
-      sts4(L + c * stride + j, o);
+      sts4(dst + (k0 + r) * stride, o);
     }
+  };
+  issue4(0, a0, a1, a2, a3);
+#pragma unroll 1
+  for (int k0 = 0; k0 < 32; k0 += 8) {
+    tmem_ld_wait(a0, a1); tmem_ld_wait(a2, a3);
+    issue4(k0 + 4, b0, b1, b2, b3);
+    compute4(k0, a0, a1, a2, a3);
+    tmem_ld_wait(b0, b1); tmem_ld_wait(b2, b3);
+    if (k0 + 8 < 32) issue4(k0 + 8, a0, a1, a2, a3);
+    compute4(k0 + 4, b0, b1, b2, b3);
   }
 }
 
@@ -521,7 +539,11 @@ __global__ void __launch_bounds__(256, 1) sc5_kernel(const float *__restrict__ l
   static_assert(M >= 10 && M <= 13, "sc5: n = 1024 .. 8192");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int N = 1 << M, NW = N >> 5, NWS = NW + 1, N64 = N >> 7, stride = 132;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  // warp index and everything derived from the frozen pattern go through a lane-0 broadcast: the values are warp
+  // uniform anyway, but only the shuffle lets the compiler KNOW it -- branches on them become uniform branches instead of
+  // potentially divergent ones that need a convergence barrier each (the 128-leaf subtree nests a dozen of them; when the
+  // barrier registers run out the compiler spills them with BMOV and the subtree phase gets 1.5x slower)
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(FULLMASK, tid >> 5, 0), nwarps = blockDim.x >> 5;
   Sc5Layout lay = sc5_layout(M, nwarps, 0);
   Pool *P = reinterpret_cast<Pool *>(smem_raw);
   uint32_t *fmask = reinterpret_cast<uint32_t *>(smem_raw + lay.fmask_off);
@@ -565,11 +587,12 @@ __global__ void __launch_bounds__(256, 1) sc5_kernel(const float *__restrict__ l
     const int nvalid = (int)((B - cw0) < 32 ? (B - cw0) : 32);
 #pragma unroll 1
     for (int i = 0; i < N64; ++i) {               // 128-leaf blocks, left to right
+      const bool zero_blk = __shfl_sync(FULLMASK, (int)nz[i], 0) != 0;      // warp uniform, and known to be
       if ((i & 1) == 0) {
         // a new stage-8 node starts here.  S = stage of the node entered at block i (the root, or the right child whose left
         // sibling has just finished); nodes of stage >= 8 are always materialised (rate-0 is only exploited per block)
         const int S = (i == 0) ? M : 7 + (__ffs(i) - 1);
-        const bool dead = nz[i] && nz[i + 1];       // nobody will read this stage-8 node
+        const bool dead = __shfl_sync(FULLMASK, (int)(nz[i] & nz[i + 1]), 0) != 0;       // nobody will read this stage-8 node
         if (S == M) {
           descent<M - 8, false, true>(logit + cw0 * (int64_t)N, nvalid, beta, NWS, 0, scr, tm_base, smem_raw, priv_unit0, lane, false);
         } else if (S == M - 1) {
@@ -587,62 +610,96 @@ __global__ void __launch_bounds__(256, 1) sc5_kernel(const float *__restrict__ l
           }
         }
         __syncwarp();
-        SC5_T(0);
-        if (!nz[i]) {
+        if (S >= M - 1) SC5_T(0); else SC5_T(1);
+        if (!zero_blk) {
           step_tmem<false>(L, beta, stride, NWS, lane, tm_base, 0);
           __syncwarp();
         }
         SC5_T(2);
-      } else if (!nz[i]) {
+      } else if (!zero_blk) {
         step_tmem<true>(L, beta, stride, NWS, lane, tm_base, 4 * (i - 1));
         __syncwarp();
-        SC5_T(1);
+        SC5_T(2);
       }
-      if (nz[i]) {
+      if (zero_blk) {
         for (int q = lane; q < 128; q += 32) beta[(q >> 2) * NWS + 4 * i + (q & 3)] = 0u;
       } else {
         const uint32_t *fmw = fmask + 4 * i;
-        const uint4 b = bottom128(L + lane * stride, (uint64_t)fmw[0] | ((uint64_t)fmw[1] << 32),
-                                  (uint64_t)fmw[2] | ((uint64_t)fmw[3] << 32));
+        const uint32_t f0 = __shfl_sync(FULLMASK, fmw[0], 0), f1 = __shfl_sync(FULLMASK, fmw[1], 0);
+        const uint32_t f2 = __shfl_sync(FULLMASK, fmw[2], 0), f3 = __shfl_sync(FULLMASK, fmw[3], 0);
+        const uint4 b = bottom128(L + lane * stride, (uint64_t)f0 | ((uint64_t)f1 << 32), (uint64_t)f2 | ((uint64_t)f3 << 32));
         uint32_t *bp = beta + lane * NWS + 4 * i;
         bp[0] = b.x; bp[1] = b.y; bp[2] = b.z; bp[3] = b.w;
       }
       __syncwarp();
       SC5_T(3);
-      {  // merge partial sums upward while the finished node is a right child: [bl ^ br, br] (polar_sc.py:83-89)
+      {  // merge partial sums upward while the finished node is a right child: [bl ^ br, br] (polar_sc.py:83-89).
+         // Lane c owns the partial-sum row of codeword c (odd row stride: conflict free); the cooperative readers (g bits
+         // of the tensor-memory steps and the descents) come after the __syncwarp below.
+        uint32_t *bw = beta + lane * NWS;
         int lv = 0, a = i;
         while (lv < M - 7 && ((a >> lv) & 1)) {
           const int nwd = 4 << lv, left = a - (1 << lv);
-          for (int q = lane; q < 32 * nwd; q += 32) {
-            const int c = q / nwd, w = q & (nwd - 1);
-            beta[c * NWS + 4 * left + w] ^= beta[c * NWS + 4 * a + w];
+#pragma unroll 1
+          for (int w = 0; w < nwd; w += 4) {          // loads first: the compiler cannot prove the two ranges distinct
+            const uint32_t r0 = bw[4 * a + w], r1 = bw[4 * a + w + 1], r2 = bw[4 * a + w + 2], r3 = bw[4 * a + w + 3];
+            const uint32_t l0 = bw[4 * left + w], l1 = bw[4 * left + w + 1], l2 = bw[4 * left + w + 2], l3 = bw[4 * left + w + 3];
+            bw[4 * left + w] = l0 ^ r0; bw[4 * left + w + 1] = l1 ^ r1; bw[4 * left + w + 2] = l2 ^ r2; bw[4 * left + w + 3] = l3 ^ r3;
           }
-          __syncwarp();
           a = left; ++lv;
         }
+        __syncwarp();
       }
       SC5_T(4);
     }
     // beta now holds the re-encoded codeword x_hat of every codeword; the decisions are u = T(x_hat)
     // (my_sn/fec/polar/enc.py:85-96 is an involution): 5 stages inside each word, M-5 across words.
-    for (int q = lane; q < 32 * NW; q += 32) {
-      const int c = q / NW, w = q % NW;
-      beta[c * NWS + w] = ptransform<5>(beta[c * NWS + w]);
-    }
-    __syncwarp();
-#pragma unroll 1
-    for (int st = 0; st < M - 5; ++st) {
-      for (int q = lane; q < 32 * (NW / 2); q += 32) {
-        const int c = q / (NW / 2), r = q % (NW / 2);
-        const int w = ((r >> st) << (st + 1)) | (r & ((1 << st) - 1));     // word index with bit st clear
-        beta[c * NWS + w] ^= beta[c * NWS + w + (1 << st)];
+    if constexpr (NW <= 64) {
+      // lane c transforms the row of codeword c entirely in registers and writes its NW words itself
+      uint32_t *bw = beta + lane * NWS;
+      uint32_t w[NW];
+#pragma unroll
+      for (int t = 0; t < NW; ++t) w[t] = ptransform<5>(bw[t]);
+#pragma unroll
+      for (int st = 0; st < M - 5; ++st)
+#pragma unroll
+        for (int t = 0; t < NW; ++t)
+          if (!(t & (1 << st))) w[t] ^= w[t + (1 << st)];
+      if (u_packed && lane < nvalid) {
+        uint32_t *dst = u_packed + (cw0 + lane) * NW;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+          for (int t = 0; t < NW; t += 4) __stcs(reinterpret_cast<uint4 *>(dst + t), make_uint4(w[t], w[t + 1], w[t + 2], w[t + 3]));
+        } else {
+#pragma unroll
+          for (int t = 0; t < NW; ++t) dst[t] = w[t];
+        }
+      }
+      if (u_info) {
+#pragma unroll
+        for (int t = 0; t < NW; ++t) bw[t] = w[t];
       }
       __syncwarp();
-    }
-    if (u_packed) {
+    } else {
       for (int q = lane; q < 32 * NW; q += 32) {
         const int c = q / NW, w = q % NW;
-        if (c < nvalid) u_packed[(cw0 + c) * NW + w] = beta[c * NWS + w];
+        beta[c * NWS + w] = ptransform<5>(beta[c * NWS + w]);
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int st = 0; st < M - 5; ++st) {
+        for (int q = lane; q < 32 * (NW / 2); q += 32) {
+          const int c = q / (NW / 2), r = q % (NW / 2);
+          const int w = ((r >> st) << (st + 1)) | (r & ((1 << st) - 1));     // word index with bit st clear
+          beta[c * NWS + w] ^= beta[c * NWS + w + (1 << st)];
+        }
+        __syncwarp();
+      }
+      if (u_packed) {
+        for (int q = lane; q < 32 * NW; q += 32) {
+          const int c = q / NW, w = q % NW;
+          if (c < nvalid) u_packed[(cw0 + c) * NW + w] = beta[c * NWS + w];
+        }
       }
     }
     if (u_info) {
