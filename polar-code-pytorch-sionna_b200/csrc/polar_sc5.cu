@@ -1,8 +1,8 @@
 // polar_sc5.cu -- SC decoder for n = 1024 .. 8192: warp-autonomous like polar_sc4.cu, with
 //   (1) every global read of the top stages STAGED THROUGH SHARED MEMORY BY THE TMA ENGINE (cp.async.bulk + mbarrier):
-//       a ring of 4 KB slots shared by the warps of the CTA, up to 6 slots (24 KB) in flight per warp.  ncu of sc4 showed
-//       the row passes waiting on register-landing loads whose scoreboards serialise (8 KB in flight per warp); a bulk
-//       copy needs no register and no scoreboard, so the passes run at the SM's share of the HBM bandwidth instead;
+//       four 4 KB slots per warp (its own stage-7 buffer, dead during a descent), 16 KB in flight per descending warp.
+//       ncu of the register-landing version showed the row passes waiting on loads whose scoreboards serialise (8 KB in
+//       flight per warp); a bulk copy needs no register and no scoreboard;
 //   (2) a scratch HIERARCHY for the stages that do not fit on chip: the stage-8 node of every codeword lives in tensor
 //       memory (256 columns per warp -> 8 warps per SM for every n), stage 7 + partial sums in shared memory, the
 //       128-leaf subtrees in registers -- and the live node of each stage 9 .. m-1 in a per-warp global scratch
@@ -71,10 +71,8 @@ __device__ unsigned long long g_sc5_dbg[8];
 namespace {
 
 constexpr unsigned FULLMASK = 0xFFFFFFFFu;
-constexpr int kSlotFloats = 1024, kSlotBytes = 4096, kMaxSlots = 32;
-constexpr int kPrivSlots = 4;        // the warp's own stage-7 buffer (32 x 132 floats) is dead during a descent: 4 private slots
-constexpr int kMaxPool = 4;          // + up to this many from the shared pool (even count)
-constexpr int kUnits = 232;          // shared memory in 1 KB units: a staging slot is named by the unit it starts at
+constexpr int kSlotFloats = 1024, kSlotBytes = 4096;
+constexpr int kSlots = 4;            // staging slots per warp = its own stage-7 buffer (32 x 132 floats), dead during a descent
 constexpr int kHeaderBytes = 4096;
 
 #define SC5_T(slot)                                                                   \
@@ -84,34 +82,27 @@ constexpr int kHeaderBytes = 4096;
     }                                                                                 \
   } while (0)
 
-struct Pool {                       // control block of the staging ring (start of shared memory)
-  unsigned long long bar[kUnits];   // one mbarrier per possible slot start (1 KB unit); only slot starts are used
-  uint32_t phase[kUnits];           // parity the NEXT completion of bar[u] will have; touched by the slot's owner only
-  uint32_t free_mask;               // bit s set <=> pool slot s is free
-  uint32_t pool_unit0;              // 1 KB unit of pool slot 0 (pool slot s starts at unit pool_unit0 + 4 s)
+struct Ctl {                        // control block (start of shared memory)
+  unsigned long long bar[8 * kSlots];   // mbarrier of staging slot j of warp w at [kSlots w + j]
   uint32_t tm_addr;                 // tcgen05.alloc result
-  uint32_t pad;
+  uint32_t pad[3];
 };
-static_assert(sizeof(Pool) + 1024 + 64 <= kHeaderBytes, "sc5: header");
+static_assert(sizeof(Ctl) + 1024 + 64 <= kHeaderBytes, "sc5: header");
 
 struct Sc5Layout {
-  int nw, nws, n64, stride, nslots;
-  size_t fmask_off, nz_off, warp_off, per_warp, slots_off, total;
+  int nw, nws, n64, stride;
+  size_t fmask_off, nz_off, warp_off, per_warp, total;
 };
-__host__ __device__ inline Sc5Layout sc5_layout(int m, int warps, size_t max_smem) {
+__host__ __device__ inline Sc5Layout sc5_layout(int m, int warps) {
   Sc5Layout l;
   const int n = 1 << m;
   l.nw = n >> 5; l.nws = l.nw + 1; l.n64 = n >> 7;
   l.stride = 128 + 4;                                   // stage-7 row of a codeword; stride/4 is odd
-  l.fmask_off = (sizeof(Pool) + 15) / 16 * 16;
+  l.fmask_off = (sizeof(Ctl) + 15) / 16 * 16;
   l.nz_off = l.fmask_off + (size_t)l.nw * 4;
-  l.warp_off = kHeaderBytes;                            // per-warp region: stage-7 rows (= 4 private slots), then partial sums
-  l.per_warp = ((size_t)32 * l.stride * 4 + (size_t)32 * l.nws * 4 + 1023) / 1024 * 1024;
-  l.slots_off = l.warp_off + (size_t)warps * l.per_warp;
-  long long ns = ((long long)max_smem - (long long)l.slots_off) / kSlotBytes;
-  if (ns > kMaxSlots) ns = kMaxSlots;
-  l.nslots = ns < 0 ? 0 : (int)ns;
-  l.total = l.slots_off + (size_t)l.nslots * kSlotBytes;
+  l.warp_off = kHeaderBytes;                            // per-warp region: stage-7 rows (= the staging slots), then partial sums
+  l.per_warp = ((size_t)32 * l.stride * 4 + (size_t)32 * l.nws * 4 + 127) / 128 * 128;
+  l.total = l.warp_off + (size_t)warps * l.per_warp;
   return l;
 }
 
@@ -212,122 +203,74 @@ PDEV void tmem_ld_wait(Tm8 &a, Tm8 &b) {   // the registers are defined only aft
 PDEV float4 tm_lo(const Tm8 &v) { return make_float4(u2f(v.r[0]), u2f(v.r[1]), u2f(v.r[2]), u2f(v.r[3])); }
 PDEV float4 tm_hi(const Tm8 &v) { return make_float4(u2f(v.r[4]), u2f(v.r[5]), u2f(v.r[6]), u2f(v.r[7])); }
 
-// ---- the staging ring ----------------------------------------------------------------------------------------------
+// ---- staging ------------------------------------------------------------------------------------------------------
 // While a warp runs a descent its own stage-7 buffer is dead (it is rewritten by the tensor-memory step that follows), so
-// it doubles as kPrivSlots PRIVATE staging slots: every warp always has 16 KB in flight without asking anybody.  On top
-// of that it takes an even number (0 .. kMaxPool) of free slots from the pool the CTA's spare shared memory provides --
-// without waiting -- and gives them back at the end of the pass.  A slot is named by the 1 KB unit of shared memory it
-// starts at (data at smem + 1024 u, mbarrier Pool::bar[u]).  units: 8 bits per held slot (private first); par: bit r =
-// parity the next completion of held slot r will have (a register during the pass, Pool::phase between passes).
-PDEV int pool_acquire(Pool *P, unsigned long long &units, uint32_t &par, const uint32_t priv_unit0, const int lane) {
-  unsigned long long got_u = 0;
-  uint32_t got_par = 0;
-  int got = 0;
-  if (lane == 0) {
-    for (int j = 0; j < kPrivSlots; ++j) got_u |= (unsigned long long)(priv_unit0 + 4 * j) << (8 * j);
-    got = kPrivSlots;
-    const uint32_t u0 = P->pool_unit0;
-    while (got < kPrivSlots + kMaxPool) {
-      const uint32_t m = *reinterpret_cast<volatile uint32_t *>(&P->free_mask);
-      if (!m) break;
-      const int s = __ffs(m) - 1;
-      const uint32_t old = atomicAnd(&P->free_mask, ~(1u << s));
-      if (old & (1u << s)) { got_u |= (unsigned long long)(u0 + 4 * s) << (8 * got); ++got; }
-    }
-    if (got & 1) {                                    // odd: give the last one back
-      --got;
-      atomicOr(&P->free_mask, 1u << (((uint32_t)(got_u >> (8 * got)) & 255u) - u0) / 4);
-      got_u &= ~(255ull << (8 * got));
-    }
-    __threadfence_block();
-    for (int i = 0; i < got; ++i)
-      got_par |= (*reinterpret_cast<volatile uint32_t *>(&P->phase[(got_u >> (8 * i)) & 255u]) & 1u) << i;
-  }
-  units = __shfl_sync(FULLMASK, got_u, 0);
-  par = __shfl_sync(FULLMASK, got_par, 0);
-  return __shfl_sync(FULLMASK, got, 0);
-}
-PDEV void pool_release(Pool *P, const unsigned long long units, const uint32_t par, const int cnt, const int lane) {
-  __syncwarp();
-  if (lane == 0) {
-    uint32_t m = 0;
-    const uint32_t u0 = P->pool_unit0;
-    for (int i = 0; i < cnt; ++i) {
-      const uint32_t u = (uint32_t)(units >> (8 * i)) & 255u;
-      P->phase[u] = (par >> i) & 1u;
-      if (i >= kPrivSlots) m |= 1u << ((u - u0) / 4);
-    }
-    __threadfence_block();
-    if (m) atomicOr(&P->free_mask, m);
-  }
-}
-
+// it serves as kSlots = 4 staging slots of 4 KB: 16 KB of bulk copies in flight per descending warp, no sharing, no
+// atomics.  (A pool of extra slots in the CTA's spare shared memory, shared by the warps, was measured and removed: with
+// 2 or 4 more slots per warp the passes were SLOWER -- the memory system, not the number of requests in flight, bounds
+// them.)  Each slot has its own mbarrier; `par` holds the parity its next completion will have, kept by the warp in a
+// register across descents.
+//
 // Fused descent (file header).  D = stages between the source (stage 8 + D: channel row or scratch node) and the stage-8
 // node that ends in tensor memory; FIRST_G: the first update is g with the partial sums of the left sibling (entering a
 // right child), else f (root); FROM_CH: the source is the channel (logits = -LLR, rows past `nvalid` repeat the last one).
-// Sub-unit of the staging stream = 4 KB (2 KB for D = 1) of ONE codeword:
-//   D <= 2: the whole source node; lane l owns columns {4l..4l+3} and {4l+128..} of every 256-column block;
+// Sub-unit of the staging stream = one 4 KB slot:
+//   D == 1: the source nodes (512 floats) of TWO consecutive codewords (they are adjacent in the scratch);
+//   D == 2: the whole source node of one codeword; lane l owns columns {4l..4l+3} and {4l+128..} of every 256-column block;
 //   D >= 3: one half h of the 256 columns (lane l: columns 128h + 4l..+3) of 8 source blocks {4q+r, 2^(D-1)+4q+r : r < 4}
-//           -- exactly the operands of the first update of 4 blocks -- gathered by 8 bulk copies of 512 B.
-// A step consumes TWO sub-units (two codewords, or the two column halves of one) so that two independent dependency
-// chains are in flight between the barrier wait and the stores: the warp shares its scheduler with one other warp only.
+//           of one codeword -- exactly the operands of the first update of 4 blocks -- gathered by 8 bulk copies of 512 B.
+// A step consumes TWO slots so that several independent dependency chains are in flight between the barrier wait and the
+// stores: the warp shares its scheduler with one other warp only.
 // Scratch of stage t (9 <= t < 8 + D) for this warp: scr + 32 (2^t - 512) + c 2^t  (c = codeword in the batch).
 // All addresses that advance with the codeword are kept as running pointers (the first version recomputed them per use
 // and spent more integer instructions on that than on the f / g arithmetic).
 template <int D, bool FIRST_G, bool FROM_CH>
 __device__ __noinline__ void descent(const float *__restrict__ src, const int nvalid, const uint32_t *beta, const int nws,
-                                     const int left_word, float *scr, const uint32_t tm_base, unsigned char *smem,
-                                     const uint32_t priv_unit0, const int lane, const bool discard) {
+                                     const int left_word, float *scr, const uint32_t tm_base, float *Lw, const uint32_t bar_a,
+                                     uint32_t &par, const int lane, const bool discard) {
   constexpr int NB = 1 << D;                       // 256-column source blocks per codeword
   constexpr int HB = NB / 2;                       // blocks of the stage 8+D-1 node
   constexpr int SRC = 256 * NB;                    // floats per codeword in the source
-  constexpr bool WIDE = D <= 2;                    // whole node per sub-unit
+  constexpr bool WIDE = D <= 2;                    // whole node(s) per slot
+  constexpr int CPS = D == 1 ? 2 : 1;              // codewords per slot (WIDE)
   constexpr int NQ = WIDE ? 1 : (1 << (D - 3));    // steps per codeword (D >= 3)
-  constexpr int K = WIDE ? 32 : 64 * NQ;           // sub-units per pass
-  constexpr uint32_t SUB_BYTES = WIDE ? SRC * 4 : 4096;
+  constexpr int K = WIDE ? 32 / CPS : 64 * NQ;     // slots per pass
   constexpr int T1 = 8 + D - 1;                    // stage of the node the first update produces
-  Pool *P = reinterpret_cast<Pool *>(smem);
   const uint64_t pol_src = l2_policy_evict_first();
   const uint64_t pol_s9 = l2_policy_evict_last(), pol_sx = l2_policy_evict_normal();
   if (!FROM_CH) asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy scratch writes -> bulk-copy reads
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // the stage-7 buffer (generic writes) becomes staging space
   __syncwarp();
-  unsigned long long units;
-  uint32_t par;
-  const int cnt = pool_acquire(P, units, par, priv_unit0, lane);
-  const uint32_t smem_a = smem_u32(smem), bar_a = smem_u32(&P->bar[0]);
-  auto unit_of = [&](const int ring) -> uint32_t { return (uint32_t)(units >> (8 * ring)) & 255u; };
+  const uint32_t slot_a = smem_u32(Lw);
 
-  // refill the held slots ring, ring+1 with sub-units k, k+1 (all lanes call it)
+  // refill slots ring, ring+1 (ring in {0, 2}) with sub-units k, k+1 (all lanes call it)
   auto issue2 = [&](const int k, const int ring) {
     if (WIDE) {
       if (lane < 2) {
-        const uint32_t u = unit_of(ring + lane);
-        int c = k + lane;
+        const int s = ring + lane;
+        int c = (k + lane) * CPS;
         if (FROM_CH && c >= nvalid) c = nvalid - 1;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a + 8 * u), "r"(SUB_BYTES) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a + 8 * s), "r"(4096) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                     ::"r"(smem_a + 1024 * u), "l"(src + (size_t)c * SRC), "r"(SUB_BYTES), "r"(bar_a + 8 * u), "l"(pol_src) : "memory");
+                     ::"r"(slot_a + 4096 * s), "l"(src + (size_t)c * SRC), "r"(4096), "r"(bar_a + 8 * s), "l"(pol_src) : "memory");
       }
     } else {
       if (lane < 2)
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a + 8 * unit_of(ring + lane)), "r"(SUB_BYTES) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a + 8 * (ring + lane)), "r"(4096) : "memory");
       __syncwarp();
       if (lane < 16) {                               // lanes 0..7: the 8 pieces of sub-unit k (h = 0), 8..15: of k+1 (h = 1)
-        const int h = lane >> 3, p = lane & 7;
-        const uint32_t u = unit_of(ring + h);
+        const int h = lane >> 3, p = lane & 7, s = ring + h;
         int c = k / (2 * NQ);
         const int q = (k >> 1) % NQ;
         if (FROM_CH && c >= nvalid) c = nvalid - 1;
         const int blk = (p & 3) + 4 * q + ((p >> 2) ? HB : 0);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                     ::"r"(smem_a + 1024 * u + 512 * p), "l"(src + (size_t)c * SRC + blk * 256 + h * 128), "r"(512), "r"(bar_a + 8 * u),
+                     ::"r"(slot_a + 4096 * s + 512 * p), "l"(src + (size_t)c * SRC + blk * 256 + h * 128), "r"(512), "r"(bar_a + 8 * s),
                      "l"(pol_src) : "memory");
       }
     }
   };
-  auto wait = [&](const int ring) -> const float * {
-    const uint32_t u = unit_of(ring);
+  auto wait = [&](const int s) -> const float * {
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
@@ -336,11 +279,12 @@ __device__ __noinline__ void descent(const float *__restrict__ src, const int nv
         "@P1 bra SC5_DONE;\n\t"
         "bra SC5_WAIT;\n\t"
         "SC5_DONE:\n\t"
-        "}" ::"r"(bar_a + 8 * u), "r"((par >> ring) & 1u), "r"(0x989680u) : "memory");
-    return reinterpret_cast<const float *>(smem + 1024 * u);
+        "}" ::"r"(bar_a + 8 * s), "r"((par >> s) & 1u), "r"(0x989680u) : "memory");
+    return Lw + s * kSlotFloats;
   };
 
-  for (int r = 0; r < cnt && r < K; r += 2) issue2(r, r);
+  issue2(0, 0);
+  issue2(2, 2);
   int ring = 0;
   const int col = 4 * lane;                                            // this lane's columns: col .. col+3 (+128 for the upper half)
   float *st1 = scr + (size_t)32 * ((1 << T1) - 512) + col;            // stage T1 scratch, advances by one codeword per unit
@@ -348,20 +292,22 @@ __device__ __noinline__ void descent(const float *__restrict__ src, const int nv
   const int sh = col & 31;                                              // (columns col and col+128 share the bit position)
   const float *dp = src + lane * 32;                                    // discard cursor (scratch sources only)
   if constexpr (WIDE) {
+    constexpr int CW = 2 * CPS;                      // codewords per step
+    int tcol = 0;                                    // tensor-memory column of the step's first codeword
 #pragma unroll 1
-    for (int c0 = 0; c0 < 32; c0 += 2) {             // two codewords per step
+    for (int k = 0; k < K; k += 2) {
       const float *sl[2];
       sl[0] = wait(ring); sl[1] = wait(ring + 1);
-      float4 v[2][2][NB];
+      float4 v[CW][2][NB];
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+      for (int u = 0; u < CW; ++u)
 #pragma unroll
         for (int e = 0; e < 2; ++e)
 #pragma unroll
-          for (int i = 0; i < NB; ++i) v[u][e][i] = lds4(sl[u] + i * 256 + col + 128 * e);
-      float4 out[2][2];
+          for (int i = 0; i < NB; ++i) v[u][e][i] = lds4(sl[u / CPS] + (u % CPS) * SRC + i * 256 + col + 128 * e);
+      float4 out[CW][2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < CW; ++u) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           float4 r1[HB];
@@ -379,18 +325,18 @@ __device__ __noinline__ void descent(const float *__restrict__ src, const int nv
           else out[u][e] = r1[0];
         }
       }
-      if (!FROM_CH && discard && lane * 32 < SRC) {    // consumed scratch lines never need to reach HBM
+      if (!FROM_CH && discard) {                       // consumed scratch lines never need to reach HBM: 2 x 4 KB = 64 lines
         asm volatile("discard.global.L2 [%0], 128;" ::"l"(dp) : "memory");
-        asm volatile("discard.global.L2 [%0], 128;" ::"l"(dp + SRC) : "memory");
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(dp + 1024) : "memory");
       }
-      st1 += 2 << T1; bp += 2 * nws; dp += 2 * SRC;
+      st1 += CW << T1; bp += CW * nws; dp += 2048;
       __syncwarp();                                    // every lane has consumed both slots
       par ^= 3u << ring;
-      if (c0 + cnt < K) issue2(c0 + cnt, ring);
-      tmem_st8(tm_base + 8 * c0, out[0][0], out[0][1]);
-      tmem_st8(tm_base + 8 * (c0 + 1), out[1][0], out[1][1]);
-      ring += 2;
-      if (ring == cnt) ring = 0;
+      if (k + kSlots < K) issue2(k + kSlots, ring);
+#pragma unroll
+      for (int u = 0; u < CW; ++u) tmem_st8(tm_base + tcol + 8 * u, out[u][0], out[u][1]);
+      tcol += 8 * CW;
+      ring ^= 2;
     }
   } else {
     const int piece = (lane >> 2) & 7, line = lane & 3;                  // discard: 2 x 8 pieces x 4 lines, two lines per lane
@@ -428,9 +374,8 @@ __device__ __noinline__ void descent(const float *__restrict__ src, const int nv
         }
         __syncwarp();
         par ^= 3u << ring;
-        if (k + cnt < K) issue2(k + cnt, ring);
-        ring += 2;
-        if (ring == cnt) ring = 0;
+        if (k + kSlots < K) issue2(k + kSlots, ring);
+        ring ^= 2;
       }
       // the rest of the left spine in registers: stage 8+D-1 -> ... -> 8; only the first of these f's can see inputs
       // outside [-30, 30] (outputs of g); everything below consumes outputs of f
@@ -451,7 +396,7 @@ __device__ __noinline__ void descent(const float *__restrict__ src, const int nv
     }
   }
   tmem_wait_st();
-  pool_release(P, units, par, cnt, lane);
+  __syncwarp();
 }
 
 // stage 8 (tensor memory, lane-private pairs) -> stage 7 in shared memory: f, or g with the partial sums of block i-1
@@ -535,7 +480,7 @@ template <int M>
 __global__ void __launch_bounds__(256, 1) sc5_kernel(const float *__restrict__ logit, const uint32_t *__restrict__ fmask_g,
                                                      int64_t B, int64_t nbatches, int dbg, float *scratch, size_t scratch_per_sm,
                                                      int scr_discard, uint32_t *__restrict__ u_packed, float *__restrict__ u_info,
-                                                     const int32_t *__restrict__ info_pos, int k, int nslots_arg) {
+                                                     const int32_t *__restrict__ info_pos, int k) {
   static_assert(M >= 10 && M <= 13, "sc5: n = 1024 .. 8192");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int N = 1 << M, NW = N >> 5, NWS = NW + 1, N64 = N >> 7, stride = 132;
@@ -544,13 +489,14 @@ __global__ void __launch_bounds__(256, 1) sc5_kernel(const float *__restrict__ l
   // potentially divergent ones that need a convergence barrier each (the 128-leaf subtree nests a dozen of them; when the
   // barrier registers run out the compiler spills them with BMOV and the subtree phase gets 1.5x slower)
   const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(FULLMASK, tid >> 5, 0), nwarps = blockDim.x >> 5;
-  Sc5Layout lay = sc5_layout(M, nwarps, 0);
-  Pool *P = reinterpret_cast<Pool *>(smem_raw);
+  Sc5Layout lay = sc5_layout(M, nwarps);
+  Ctl *P = reinterpret_cast<Ctl *>(smem_raw);
   uint32_t *fmask = reinterpret_cast<uint32_t *>(smem_raw + lay.fmask_off);
   unsigned char *nz = smem_raw + lay.nz_off;            // nz[i]: 128-leaf block i is rate-0
   float *L = reinterpret_cast<float *>(smem_raw + lay.warp_off + (size_t)warp * lay.per_warp);
   uint32_t *beta = reinterpret_cast<uint32_t *>(L + 32 * stride);
-  const uint32_t priv_unit0 = (uint32_t)((lay.warp_off + (size_t)warp * lay.per_warp) >> 10);
+  const uint32_t bar_a = smem_u32(&P->bar[kSlots * warp]);   // this warp's four slot barriers
+  uint32_t par = 0;                                          // parity the next completion of each will have
 
   if (warp == 0) {          // the CTA is alone on its SM (shared memory): take all 512 tensor-memory columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -558,9 +504,7 @@ __global__ void __launch_bounds__(256, 1) sc5_kernel(const float *__restrict__ l
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    for (int s = 0; s < kUnits; ++s) { mbar_init(&P->bar[s], 1); P->phase[s] = 0; }
-    P->pool_unit0 = (uint32_t)(lay.slots_off >> 10);
-    P->free_mask = nslots_arg >= 32 ? 0xFFFFFFFFu : ((1u << nslots_arg) - 1u);
+    for (int s = 0; s < 8 * kSlots; ++s) mbar_init(&P->bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -594,18 +538,18 @@ __global__ void __launch_bounds__(256, 1) sc5_kernel(const float *__restrict__ l
         const int S = (i == 0) ? M : 7 + (__ffs(i) - 1);
         const bool dead = __shfl_sync(FULLMASK, (int)(nz[i] & nz[i + 1]), 0) != 0;       // nobody will read this stage-8 node
         if (S == M) {
-          descent<M - 8, false, true>(logit + cw0 * (int64_t)N, nvalid, beta, NWS, 0, scr, tm_base, smem_raw, priv_unit0, lane, false);
+          descent<M - 8, false, true>(logit + cw0 * (int64_t)N, nvalid, beta, NWS, 0, scr, tm_base, L, bar_a, par, lane, false);
         } else if (S == M - 1) {
-          descent<M - 8, true, true>(logit + cw0 * (int64_t)N, nvalid, beta, NWS, 0, scr, tm_base, smem_raw, priv_unit0, lane, false);
+          descent<M - 8, true, true>(logit + cw0 * (int64_t)N, nvalid, beta, NWS, 0, scr, tm_base, L, bar_a, par, lane, false);
         } else {
           const int left_word = 4 * (i - (1 << (S - 7)));      // the left sibling's partial sums start at that block
           const float *sp = scr + (size_t)32 * ((1 << (S + 1)) - 512);
           const bool dis = scr_discard != 0;
           switch (S) {                                         // source = scratch node of stage S+1, D = S+1-8
-            case 8: if (!dead) descent<1, true, false>(sp, 32, beta, NWS, left_word, scr, tm_base, smem_raw, priv_unit0, lane, dis); break;
-            case 9: if (M > 10) descent<(M > 10 ? 2 : 1), true, false>(sp, 32, beta, NWS, left_word, scr, tm_base, smem_raw, priv_unit0, lane, dis); break;
-            case 10: if (M > 11) descent<(M > 11 ? 3 : 1), true, false>(sp, 32, beta, NWS, left_word, scr, tm_base, smem_raw, priv_unit0, lane, dis); break;
-            case 11: if (M > 12) descent<(M > 12 ? 4 : 1), true, false>(sp, 32, beta, NWS, left_word, scr, tm_base, smem_raw, priv_unit0, lane, dis); break;
+            case 8: if (!dead) descent<1, true, false>(sp, 32, beta, NWS, left_word, scr, tm_base, L, bar_a, par, lane, dis); break;
+            case 9: if (M > 10) descent<(M > 10 ? 2 : 1), true, false>(sp, 32, beta, NWS, left_word, scr, tm_base, L, bar_a, par, lane, dis); break;
+            case 10: if (M > 11) descent<(M > 11 ? 3 : 1), true, false>(sp, 32, beta, NWS, left_word, scr, tm_base, L, bar_a, par, lane, dis); break;
+            case 11: if (M > 12) descent<(M > 12 ? 4 : 1), true, false>(sp, 32, beta, NWS, left_word, scr, tm_base, L, bar_a, par, lane, dis); break;
             default: break;
           }
         }
@@ -746,24 +690,26 @@ int launch_sc5_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t 
   constexpr int N = 1 << M;
   int wmax = 8;                                         // tensor memory: 256 columns per warp, 512 per lane quarter
   if (warps <= 0 || warps > wmax) warps = wmax;
-  while (warps > 1 && (sc5_layout(M, warps, max_smem).total > (size_t)max_smem ||
+  while (warps > 1 && (sc5_layout(M, warps).total > (size_t)max_smem ||
                        (size_t)warps * 32 * (N - 512) * 4 > kScScratchPerSm)) --warps;
-  const Sc5Layout lay = sc5_layout(M, warps, max_smem);
+  const Sc5Layout lay = sc5_layout(M, warps);
   if (lay.total > (size_t)max_smem) return set_error(POLAR_ENOMEM, "sc: n=%d needs more shared memory per CTA than the device has", N);
   float *scratch = sc_scratch();
   if (!scratch)
     return set_error(POLAR_EINVAL, "sc: n=%d needs the per-device stage scratch -- call polar_init(device) once before decoding", N);
   auto kern = sc5_kernel<M>;
   // one persistent CTA per SM: it takes all 512 tensor-memory columns, so a second CTA must never become resident on the
-  // same SM (the request is far above half of the SM's shared memory)
-  POLAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+  // same SM: the shared-memory request is padded above half of the SM's
+  size_t smem = lay.total;
+  if (smem < (size_t)116 * 1024) smem = (size_t)116 * 1024;
+  POLAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = device_sm_count();
   const int64_t nbatches = (B + 31) / 32;
   int64_t grid = (nbatches + warps - 1) / warps;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, warps * 32, lay.total, st>>>(logit, fmask, B, nbatches, env_int("POLAR_SC3_DBG", 0), scratch, kScScratchPerSm,
-                                                      env_int("POLAR_SC4_DISCARD", 1), u_packed, u_info, info_pos, k, lay.nslots);
+  kern<<<(unsigned)grid, warps * 32, smem, st>>>(logit, fmask, B, nbatches, env_int("POLAR_SC3_DBG", 0), scratch, kScScratchPerSm,
+                                                      env_int("POLAR_SC4_DISCARD", 1), u_packed, u_info, info_pos, k);
   count_launch();
   POLAR_CHECK_LAUNCH("sc5_kernel");
   return POLAR_OK;
