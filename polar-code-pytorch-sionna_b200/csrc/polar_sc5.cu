@@ -72,8 +72,8 @@ namespace {
 
 constexpr unsigned FULLMASK = 0xFFFFFFFFu;
 constexpr int kSlotFloats = 1024, kSlotBytes = 4096;
-constexpr int kSlots = 4;            // staging slots per warp = its own stage-7 buffer (32 x 132 floats), dead during a descent
-constexpr int kHeaderBytes = 4096;
+constexpr int kSlots = 6;            // at most: 4 = the warp's own stage-7 buffer (dead during a descent), 6 where spare shared memory allows
+constexpr int kHeaderBytes = 1024;   // + frozen mask words and block flags for n > 1024 (sc5_layout)
 
 #define SC5_T(slot)                                                                   \
   do {                                                                                \
@@ -87,21 +87,23 @@ struct Ctl {                        // control block (start of shared memory)
   uint32_t tm_addr;                 // tcgen05.alloc result
   uint32_t pad[3];
 };
-static_assert(sizeof(Ctl) + 1024 + 64 <= kHeaderBytes, "sc5: header");
+static_assert(sizeof(Ctl) + 128 + 8 <= kHeaderBytes, "sc5: header");
 
 struct Sc5Layout {
-  int nw, nws, n64, stride;
-  size_t fmask_off, nz_off, warp_off, per_warp, total;
+  int nw, nws, n64, stride, slots;
+  size_t fmask_off, nz_off, warp_off, per_warp, beta_off, total;
 };
-__host__ __device__ inline Sc5Layout sc5_layout(int m, int warps) {
+__host__ __device__ inline Sc5Layout sc5_layout(int m, int warps, int slots) {
   Sc5Layout l;
   const int n = 1 << m;
-  l.nw = n >> 5; l.nws = l.nw + 1; l.n64 = n >> 7;
+  l.nw = n >> 5; l.nws = l.nw + 1; l.n64 = n >> 7; l.slots = slots;
   l.stride = 128 + 4;                                   // stage-7 row of a codeword; stride/4 is odd
   l.fmask_off = (sizeof(Ctl) + 15) / 16 * 16;
   l.nz_off = l.fmask_off + (size_t)l.nw * 4;
-  l.warp_off = kHeaderBytes;                            // per-warp region: stage-7 rows (= the staging slots), then partial sums
-  l.per_warp = ((size_t)32 * l.stride * 4 + (size_t)32 * l.nws * 4 + 127) / 128 * 128;
+  l.warp_off = (l.nz_off + (size_t)l.n64 + 1023) / 1024 * 1024;
+  // per-warp region: staging slots (the first 32 x 132 floats double as the stage-7 rows), then the partial sums
+  l.beta_off = (size_t)slots * kSlotBytes > (size_t)32 * l.stride * 4 ? (size_t)slots * kSlotBytes : (size_t)32 * l.stride * 4;
+  l.per_warp = (l.beta_off + (size_t)32 * l.nws * 4 + 127) / 128 * 128;
   l.total = l.warp_off + (size_t)warps * l.per_warp;
   return l;
 }
@@ -224,7 +226,7 @@ PDEV float4 tm_hi(const Tm8 &v) { return make_float4(u2f(v.r[4]), u2f(v.r[5]), u
 // Scratch of stage t (9 <= t < 8 + D) for this warp: scr + 32 (2^t - 512) + c 2^t  (c = codeword in the batch).
 // All addresses that advance with the codeword are kept as running pointers (the first version recomputed them per use
 // and spent more integer instructions on that than on the f / g arithmetic).
-template <int D, bool FIRST_G, bool FROM_CH>
+template <int D, bool FIRST_G, bool FROM_CH, int NS>
 __device__ __noinline__ void descent(const float *__restrict__ src, const int nvalid, const uint32_t *beta, const int nws,
                                      const int left_word, float *scr, const uint32_t tm_base, float *Lw, const uint32_t bar_a,
                                      uint32_t &par, const int lane, const bool discard) {
@@ -243,7 +245,7 @@ __device__ __noinline__ void descent(const float *__restrict__ src, const int nv
   __syncwarp();
   const uint32_t slot_a = smem_u32(Lw);
 
-  // refill slots ring, ring+1 (ring in {0, 2}) with sub-units k, k+1 (all lanes call it)
+  // refill slots ring, ring+1 (ring in {0, 2, ..}) with sub-units k, k+1 (all lanes call it)
   auto issue2 = [&](const int k, const int ring) {
     if (WIDE) {
       if (lane < 2) {
@@ -283,8 +285,8 @@ __device__ __noinline__ void descent(const float *__restrict__ src, const int nv
     return Lw + s * kSlotFloats;
   };
 
-  issue2(0, 0);
-  issue2(2, 2);
+#pragma unroll
+  for (int r = 0; r < NS; r += 2) issue2(r, r);
   int ring = 0;
   const int col = 4 * lane;                                            // this lane's columns: col .. col+3 (+128 for the upper half)
   float *st1 = scr + (size_t)32 * ((1 << T1) - 512) + col;            // stage T1 scratch, advances by one codeword per unit
@@ -332,11 +334,11 @@ __device__ __noinline__ void descent(const float *__restrict__ src, const int nv
       st1 += CW << T1; bp += CW * nws; dp += 2048;
       __syncwarp();                                    // every lane has consumed both slots
       par ^= 3u << ring;
-      if (k + kSlots < K) issue2(k + kSlots, ring);
+      if (k + NS < K) issue2(k + NS, ring);
 #pragma unroll
       for (int u = 0; u < CW; ++u) tmem_st8(tm_base + tcol + 8 * u, out[u][0], out[u][1]);
       tcol += 8 * CW;
-      ring ^= 2;
+      ring = (ring + 2 == NS) ? 0 : ring + 2;
     }
   } else {
     const int piece = (lane >> 2) & 7, line = lane & 3;                  // discard: 2 x 8 pieces x 4 lines, two lines per lane
@@ -374,8 +376,8 @@ __device__ __noinline__ void descent(const float *__restrict__ src, const int nv
         }
         __syncwarp();
         par ^= 3u << ring;
-        if (k + kSlots < K) issue2(k + kSlots, ring);
-        ring ^= 2;
+        if (k + NS < K) issue2(k + NS, ring);
+        ring = (ring + 2 == NS) ? 0 : ring + 2;
       }
       // the rest of the left spine in registers: stage 8+D-1 -> ... -> 8; only the first of these f's can see inputs
       // outside [-30, 30] (outputs of g); everything below consumes outputs of f
@@ -476,7 +478,7 @@ PDEV uint4 bottom128(const float *node, uint64_t fm0, uint64_t fm1) {
   return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)bc, (uint32_t)(bc >> 32));
 }
 
-template <int M>
+template <int M, int NS>
 __global__ void __launch_bounds__(256, 1) sc5_kernel(const float *__restrict__ logit, const uint32_t *__restrict__ fmask_g,
                                                      int64_t B, int64_t nbatches, int dbg, float *scratch, size_t scratch_per_sm,
                                                      int scr_discard, uint32_t *__restrict__ u_packed, float *__restrict__ u_info,
@@ -489,12 +491,12 @@ __global__ void __launch_bounds__(256, 1) sc5_kernel(const float *__restrict__ l
   // potentially divergent ones that need a convergence barrier each (the 128-leaf subtree nests a dozen of them; when the
   // barrier registers run out the compiler spills them with BMOV and the subtree phase gets 1.5x slower)
   const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(FULLMASK, tid >> 5, 0), nwarps = blockDim.x >> 5;
-  Sc5Layout lay = sc5_layout(M, nwarps);
+  Sc5Layout lay = sc5_layout(M, nwarps, NS);
   Ctl *P = reinterpret_cast<Ctl *>(smem_raw);
   uint32_t *fmask = reinterpret_cast<uint32_t *>(smem_raw + lay.fmask_off);
   unsigned char *nz = smem_raw + lay.nz_off;            // nz[i]: 128-leaf block i is rate-0
   float *L = reinterpret_cast<float *>(smem_raw + lay.warp_off + (size_t)warp * lay.per_warp);
-  uint32_t *beta = reinterpret_cast<uint32_t *>(L + 32 * stride);
+  uint32_t *beta = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(L) + lay.beta_off);
   const uint32_t bar_a = smem_u32(&P->bar[kSlots * warp]);   // this warp's four slot barriers
   uint32_t par = 0;                                          // parity the next completion of each will have
 
@@ -538,18 +540,18 @@ __global__ void __launch_bounds__(256, 1) sc5_kernel(const float *__restrict__ l
         const int S = (i == 0) ? M : 7 + (__ffs(i) - 1);
         const bool dead = __shfl_sync(FULLMASK, (int)(nz[i] & nz[i + 1]), 0) != 0;       // nobody will read this stage-8 node
         if (S == M) {
-          descent<M - 8, false, true>(logit + cw0 * (int64_t)N, nvalid, beta, NWS, 0, scr, tm_base, L, bar_a, par, lane, false);
+          descent<M - 8, false, true, NS>(logit + cw0 * (int64_t)N, nvalid, beta, NWS, 0, scr, tm_base, L, bar_a, par, lane, false);
         } else if (S == M - 1) {
-          descent<M - 8, true, true>(logit + cw0 * (int64_t)N, nvalid, beta, NWS, 0, scr, tm_base, L, bar_a, par, lane, false);
+          descent<M - 8, true, true, NS>(logit + cw0 * (int64_t)N, nvalid, beta, NWS, 0, scr, tm_base, L, bar_a, par, lane, false);
         } else {
           const int left_word = 4 * (i - (1 << (S - 7)));      // the left sibling's partial sums start at that block
           const float *sp = scr + (size_t)32 * ((1 << (S + 1)) - 512);
           const bool dis = scr_discard != 0;
           switch (S) {                                         // source = scratch node of stage S+1, D = S+1-8
-            case 8: if (!dead) descent<1, true, false>(sp, 32, beta, NWS, left_word, scr, tm_base, L, bar_a, par, lane, dis); break;
-            case 9: if (M > 10) descent<(M > 10 ? 2 : 1), true, false>(sp, 32, beta, NWS, left_word, scr, tm_base, L, bar_a, par, lane, dis); break;
-            case 10: if (M > 11) descent<(M > 11 ? 3 : 1), true, false>(sp, 32, beta, NWS, left_word, scr, tm_base, L, bar_a, par, lane, dis); break;
-            case 11: if (M > 12) descent<(M > 12 ? 4 : 1), true, false>(sp, 32, beta, NWS, left_word, scr, tm_base, L, bar_a, par, lane, dis); break;
+            case 8: if (!dead) descent<1, true, false, NS>(sp, 32, beta, NWS, left_word, scr, tm_base, L, bar_a, par, lane, dis); break;
+            case 9: if (M > 10) descent<(M > 10 ? 2 : 1), true, false, NS>(sp, 32, beta, NWS, left_word, scr, tm_base, L, bar_a, par, lane, dis); break;
+            case 10: if (M > 11) descent<(M > 11 ? 3 : 1), true, false, NS>(sp, 32, beta, NWS, left_word, scr, tm_base, L, bar_a, par, lane, dis); break;
+            case 11: if (M > 12) descent<(M > 12 ? 4 : 1), true, false, NS>(sp, 32, beta, NWS, left_word, scr, tm_base, L, bar_a, par, lane, dis); break;
             default: break;
           }
         }
@@ -690,14 +692,16 @@ int launch_sc5_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t 
   constexpr int N = 1 << M;
   int wmax = 8;                                         // tensor memory: 256 columns per warp, 512 per lane quarter
   if (warps <= 0 || warps > wmax) warps = wmax;
-  while (warps > 1 && (sc5_layout(M, warps).total > (size_t)max_smem ||
+  while (warps > 1 && (sc5_layout(M, warps, 4).total > (size_t)max_smem ||
                        (size_t)warps * 32 * (N - 512) * 4 > kScScratchPerSm)) --warps;
-  const Sc5Layout lay = sc5_layout(M, warps);
+  int ns = env_int("POLAR_SC5_SLOTS", 6);               // staging slots per warp: 6 where the spare shared memory allows
+  if (ns != 6 || sc5_layout(M, warps, 6).total > (size_t)max_smem) ns = 4;
+  const Sc5Layout lay = sc5_layout(M, warps, ns);
   if (lay.total > (size_t)max_smem) return set_error(POLAR_ENOMEM, "sc: n=%d needs more shared memory per CTA than the device has", N);
   float *scratch = sc_scratch();
   if (!scratch)
     return set_error(POLAR_EINVAL, "sc: n=%d needs the per-device stage scratch -- call polar_init(device) once before decoding", N);
-  auto kern = sc5_kernel<M>;
+  auto kern = ns == 6 ? sc5_kernel<M, 6> : sc5_kernel<M, 4>;
   // one persistent CTA per SM: it takes all 512 tensor-memory columns, so a second CTA must never become resident on the
   // same SM: the shared-memory request is padded above half of the SM's
   size_t smem = lay.total;
