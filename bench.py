@@ -473,7 +473,7 @@ def main():
         link = {"metric": "link_model_throughput_sc_n1024", "codewords_per_s": world * Bl / (ms * 1e-3),
                 "value": world * Bl / (ms * 1e-3) * k / 1e9, "unit": "Gbit/s", "ms_per_step": ms, "batch": Bl,
                 "api": "System_AWGN_model.forward(batch_size, ebno_db) -> (bits [B,k], bits_hat [B,k]) fp32 device tensors "
-                       "(polar_awgn_frontend + sc4_kernel + 2 unpack kernels per call)",
+                       "(polar_awgn_frontend + sc5_kernel + 2 unpack kernels per call)",
                 "bler": float((bits != bits_hat).any(dim=1).float().mean().item())}
         del bits, bits_hat, model
 
@@ -606,7 +606,7 @@ def main():
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     cw_rate_gpu = B / (kern_ms * 1e-3)
     issue_peak = sms * 4 * sm_clk * 1e6  # one warp instruction per scheduler and cycle
-    cnts, cnts_src = ncu_counters("sc4_kernel<10,2>")
+    cnts, cnts_src = ncu_counters("sc5_kernel<10>")
     traffic = None
     other_bounds = {"counters": cnts_src}
     if cnts and B == (1 << 20):
@@ -628,7 +628,7 @@ def main():
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "sc4_kernel<10,2> (polar_sc4.cu)", "kernel_ms": kern_ms, "bytes_per_codeword": bytes_per_cw,
+                     "kernel": "sc5_kernel<10,6> (polar_sc5.cu)", "kernel_ms": kern_ms, "bytes_per_codeword": bytes_per_cw,
                      "other_bounds": other_bounds,
                      "note": "algorithmic bytes = 4n + k/8 per codeword; achieved = B x 4160 B / mean CUDA-event time of the kernel "
                              "launches of the timed region (DESIGN.md 4.1)"},

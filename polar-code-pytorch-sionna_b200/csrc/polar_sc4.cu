@@ -295,7 +295,9 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
   constexpr int WB = 1 << (BOT - 5);                         // 32-bit words per bottom block
   constexpr int N = 1 << M, NW = N >> 5, NWS = NW + 1, N64 = N >> BOT, TOP = TM ? TS - 1 : M - 1;
   constexpr int TM_COLS_WARP = TM ? (1 << TS) : 32;         // 32 codewords x 2^TS floats / 32 lanes
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  // lane-0 broadcasts: warp index and frozen-pattern words are warp uniform, and the shuffle lets the compiler know
+  // (uniform branches instead of potentially divergent ones in the register subtrees; see polar_sc5.cu)
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(FULLMASK, tid >> 5, 0), nwarps = blockDim.x >> 5;
   const Sc4Layout lay = sc4_layout(M, TOP, BOT, nwarps);
   constexpr int stride = (2 << TOP) - (1 << BOT) + 4;   // == lay.stride, compile-time so that row offsets fold into immediates
   uint32_t *fmask = reinterpret_cast<uint32_t *>(smem_raw);
@@ -381,12 +383,13 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
         }
       } else if (BOT == 7) {
         const uint32_t *fmw = fmask + 4 * i;
-        const uint4 b = bottom128(L + lane * stride, (uint64_t)fmw[0] | ((uint64_t)fmw[1] << 32),
-                                  (uint64_t)fmw[2] | ((uint64_t)fmw[3] << 32));
+        const uint32_t f0 = __shfl_sync(FULLMASK, fmw[0], 0), f1 = __shfl_sync(FULLMASK, fmw[1], 0);
+        const uint32_t f2 = __shfl_sync(FULLMASK, fmw[2], 0), f3 = __shfl_sync(FULLMASK, fmw[3], 0);
+        const uint4 b = bottom128(L + lane * stride, (uint64_t)f0 | ((uint64_t)f1 << 32), (uint64_t)f2 | ((uint64_t)f3 << 32));
         uint32_t *bp = beta + lane * NWS + 4 * i;
         bp[0] = b.x; bp[1] = b.y; bp[2] = b.z; bp[3] = b.w;
       } else {
-        const uint2 b = bottom64(L + lane * stride, fmask[2 * i], fmask[2 * i + 1]);
+        const uint2 b = bottom64(L + lane * stride, __shfl_sync(FULLMASK, fmask[2 * i], 0), __shfl_sync(FULLMASK, fmask[2 * i + 1], 0));
         uint32_t *bp = beta + lane * NWS + 2 * i;
         bp[0] = b.x; bp[1] = b.y;
       }

@@ -1,5 +1,5 @@
-"""Quick kernel timing sweep (CUDA events) for tuning; not the bench.  Usage on the GPU box:
-   python tools/perf_probe.py sc|scl|fe [n] [B]"""
+"""Quick kernel timing sweeps (CUDA events) for tuning; not the bench.  Usage on the GPU box:
+   python tools/perf_probe.py scl|scl3|sptest|fe [n] [B]        (SC decoder: tools/sc_check.py)"""
 import os
 import sys
 import time
@@ -28,80 +28,14 @@ def timeit(fn, iters=5, warm=2):
 
 
 def main():
-    what = sys.argv[1] if len(sys.argv) > 1 else "sc"
+    what = sys.argv[1] if len(sys.argv) > 1 else "scl3"
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
     k = n // 2
     dev = torch.device("cuda", 0)
     fp = po.rm_frozen_pos(n, n - k)
     tables = dk.code_tables(fp, n, dev)
     no = po.ebnodb2no(4.0, 2, k / n)
-    if what == "sccta":
-        B = int(sys.argv[3]) if len(sys.argv) > 3 else (1 << 28) // n
-        _, _, x = dk.awgn_frontend(tables, B, no, 1234)
-        up = torch.empty((B, dk.words(n)), dtype=torch.int32, device=dev)
-        dk.set_option("POLAR_SC_MODE", int("1"))
-        for ctas in [int(v) for v in os.environ.get("CTAS", "1,2,3,4,6").split(",")]:
-            for thr in [int(v) for v in os.environ.get("THREADS", "64,128,256").split(",")]:
-                dk.set_option("POLAR_SC_CTAS", int(str(ctas))); dk.set_option("POLAR_SC_THREADS", int(str(thr)))
-                f = lambda: dk.check(dk.lib().polar_sc_decode_f32(dk.ptr(x), dk.ptr(tables.frozen_mask), n, B, dk.ptr(up), None, None, 0, dk.stream_ptr(dev)))
-                best, med = timeit(f)
-                print("SC-CTA n=%d B=%d ctas/SM=%d threads=%3d: %8.3f ms  %.3e cw/s  %.1f Gbit/s info  HBM-frac %.3f" %
-                      (n, B, ctas, thr, best, B / best * 1e3, B / best * 1e3 * k / 1e9, B / best * 1e3 * (4 * n + k / 8) / 6552.3e9), flush=True)
-    elif what == "sc4":
-        import ctypes
-        B = int(sys.argv[3]) if len(sys.argv) > 3 else (1 << 28) // n
-        _, _, x = dk.awgn_frontend(tables, B, no, 1234)
-        up = torch.empty((B, dk.words(n)), dtype=torch.int32, device=dev)
-        dk.set_option("POLAR_SC_MODE", int("3"))
-        for w in [int(v) for v in os.environ.get("WARPS", "0").split(",")]:
-            dk.set_option("POLAR_SC_WARPS_SM", int(str(w)))
-            f = lambda: dk.check(dk.lib().polar_sc_decode_f32(dk.ptr(x), dk.ptr(tables.frozen_mask), n, B, dk.ptr(up), None, None, 0, dk.stream_ptr(dev)))
-            best, med = timeit(f)
-            if os.environ.get("POLAR_SC3_DBG") == "1":
-                L = ctypes.CDLL(dk.LIB_PATH); buf = (ctypes.c_ulonglong * 8)()
-                L.polar_sc4_debug_read(buf); f(); torch.cuda.synchronize(); L.polar_sc4_debug_read(buf)
-                v = list(buf); nb = max(v[7], 1)
-                print("  warp0 cycles/batch: virt %d  g %d  f %d  bottom %d  merge %d  out %d  | total %d  batches %d" %
-                      tuple([x // nb for x in v[:7]] + [v[7]]))
-            print("SC4 n=%d B=%d warps/SM=%d: %8.3f ms  %.3e cw/s  %.1f Gbit/s info  HBM-frac %.3f" %
-                  (n, B, w, best, B / best * 1e3, B / best * 1e3 * k / 1e9, B / best * 1e3 * (4 * n + k / 8) / 6552.3e9), flush=True)
-    elif what == "sc3":
-        B = int(sys.argv[3]) if len(sys.argv) > 3 else (1 << 28) // n
-        _, _, x = dk.awgn_frontend(tables, B, no, 1234)
-        up = torch.empty((B, dk.words(n)), dtype=torch.int32, device=dev)
-        dk.set_option("POLAR_SC_MODE", int("2"))
-        for cw in [int(v) for v in os.environ.get("CWS", "32").split(",")]:
-            for ctas in [int(v) for v in os.environ.get("CTAS", "0,2,3,4").split(",")]:
-                for thr in [128]:
-                    dk.set_option("POLAR_SC_CTAS", int(str(ctas))); dk.set_option("POLAR_SC_THREADS", int(str(thr)))
-                    dk.set_option("POLAR_SC_CTA_CW", int(str(cw)))
-                    f = lambda: dk.check(dk.lib().polar_sc_decode_f32(dk.ptr(x), dk.ptr(tables.frozen_mask), n, B, dk.ptr(up), None, None, 0, dk.stream_ptr(dev)))
-                    best, med = timeit(f)
-                    if os.environ.get("POLAR_SC3_DBG") == "1":
-                        import ctypes
-                        L = ctypes.CDLL(dk.LIB_PATH); buf = (ctypes.c_ulonglong * 8)()
-                        L.polar_sc3_debug_read(buf); f(); torch.cuda.synchronize(); L.polar_sc3_debug_read(buf)
-                        v = list(buf); nb = max(v[7], 1)
-                        print("  CTA0 cycles/batch: virt %d  g %d  f %d  bottom %d  merge %d  out %d  | total %d  batches %d" %
-                              tuple([x // nb for x in v[:7]] + [v[7]]))
-                    print("SC3 n=%d B=%d cw=%d ctas/SM=%d threads=%3d bwdiv=%s: %8.3f ms  %.3e cw/s  %.1f Gbit/s info  HBM-frac %.3f" %
-                          (n, B, cw, ctas, thr, os.environ.get("POLAR_SC3_BWDIV", "sms"), best, B / best * 1e3, B / best * 1e3 * k / 1e9, B / best * 1e3 * (4 * n + k / 8) / 6552.3e9), flush=True)
-    elif what == "sc":
-        dk.set_option("POLAR_SC_MODE", int("0"))
-        B = int(sys.argv[3]) if len(sys.argv) > 3 else (1 << 28) // n
-        _, _, x = dk.awgn_frontend(tables, B, no, 1234)
-        up = torch.empty((B, dk.words(n)), dtype=torch.int32, device=dev)
-        for cw in [int(v) for v in os.environ.get("CWS", "2,4,8,16,32").split(",")]:
-            for warps in [int(v) for v in os.environ.get("WARPS", "1,2,4").split(",")]:
-                dk.set_option("POLAR_SC_CW", int(str(cw))); dk.set_option("POLAR_SC_WARPS", int(str(warps)))
-                try:
-                    f = lambda: dk.check(dk.lib().polar_sc_decode_f32(dk.ptr(x), dk.ptr(tables.frozen_mask), n, B, dk.ptr(up), None, None, 0, dk.stream_ptr(dev)))
-                    best, med = timeit(f)
-                    print("SC n=%d B=%d CW=%2d warps=%d: %8.3f ms  %.3e cw/s  %.1f Gbit/s info  HBM-frac %.3f" %
-                          (n, B, cw, warps, best, B / best * 1e3, B / best * 1e3 * k / 1e9, B / best * 1e3 * (4 * n + k / 8) / 6552.3e9), flush=True)
-                except Exception as e:
-                    print("SC CW=%d warps=%d failed: %s" % (cw, warps, e))
-    elif what == "scl":
+    if what == "scl":
         L = int(os.environ.get("L", "8"))
         B = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 15
         _, _, x = dk.awgn_frontend(tables, B, no, 1234)

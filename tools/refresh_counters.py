@@ -36,7 +36,7 @@ def capture(what, match, batch):
 def main():
     out = {"source_stamp": source_stamp(),
            "how": "ncu --metrics %s --clock-control none (tools/refresh_counters.py), second launch" % METRICS,
-           "sc4_kernel<10,2>": capture("sc", "sc4_kernel", 1 << 20),
+           "sc5_kernel<10>": capture("sc", "sc5_kernel", 1 << 20),
            "scl3_kernel<10,8>": capture("scl", "scl3_kernel", 1 << 18)}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "sc_counters.json"), "w"), indent=1)
