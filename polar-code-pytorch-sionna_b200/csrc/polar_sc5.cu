@@ -238,7 +238,9 @@ __device__ __noinline__ void descent(const float *__restrict__ src, const int nv
   constexpr int NQ = WIDE ? 1 : (1 << (D - 3));    // steps per codeword (D >= 3)
   constexpr int K = WIDE ? 32 / CPS : 64 * NQ;     // slots per pass
   constexpr int T1 = 8 + D - 1;                    // stage of the node the first update produces
-  const uint64_t pol_src = l2_policy_evict_first();
+  // channel rows are streamed (nobody comes back within the L2's reach); a scratch node must stay in the L2 until the
+  // discard that follows its only read -- reading it evict_first would get the dirty line written back before that
+  const uint64_t pol_src = FROM_CH ? l2_policy_evict_first() : (D == 1 ? l2_policy_evict_last() : l2_policy_evict_normal());
   const uint64_t pol_s9 = l2_policy_evict_last(), pol_sx = l2_policy_evict_normal();
   if (!FROM_CH) asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy scratch writes -> bulk-copy reads
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // the stage-7 buffer (generic writes) becomes staging space
@@ -712,7 +714,10 @@ int launch_sc5_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t 
   int64_t grid = (nbatches + warps - 1) / warps;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, warps * 32, smem, st>>>(logit, fmask, B, nbatches, env_int("POLAR_SC3_DBG", 0), scratch, kScScratchPerSm,
+  kern<<<(unsigned)grid, warps * 32, smem, st>>>(logit, fmask, B, nbatches, env_int("POLAR_SC3_DBG", 0), scratch,
+                                              // slots packed back to back: what this launch uses is one dense range (76 MB for
+                                              // n = 1024, L2 resident); a sparse 4 MB stride made the L2 write every line back
+                                              (size_t)warps * 32 * (N - 512) * 4,
                                                       env_int("POLAR_SC4_DISCARD", 1), u_packed, u_info, info_pos, k);
   count_launch();
   POLAR_CHECK_LAUNCH("sc5_kernel");
