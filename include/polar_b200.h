@@ -114,6 +114,16 @@ int polar_scl_decode_boxplus(const float *d_logit, const uint32_t *d_frozen_mask
                              double *d_pm_sorted, uint32_t *d_list_packed,
                              const uint32_t *d_crc_rows, int crc_len,
                              void *d_workspace, size_t workspace_bytes, void *stream);
+/* The same decoder with the reference's fast-SCL node shortcuts (use_fast_scl=True, my_sn/fec/polar/dec.py:269-306,
+ * 354-376): a rate-0 node (all leaves frozen) or REP node (only the last leaf carries information) of up to 32 leaves is
+ * not descended into -- its path-metric update is the sum of log(1+exp(-+llr)) over the node's own LLRs (for REP: one
+ * sum per value of the information bit, then the usual sort / keep L).  Exact under the boxplus f (not under min-sum, so
+ * there is no min-sum counterpart).  Same arguments and workspace. */
+int polar_scl_decode_boxplus_pruned(const float *d_logit, const uint32_t *d_frozen_mask, int n, int L, int64_t B,
+                                    uint32_t *d_best_packed, float *d_u_info_f32, const int32_t *d_info_pos, int k,
+                                    double *d_pm_sorted, uint32_t *d_list_packed,
+                                    const uint32_t *d_crc_rows, int crc_len,
+                                    void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* ---- encoder -----------------------------------------------------------------------------
  * polar_encode_packed: x = u.G over GF(2) on bit-packed rows (XOR butterfly; the transform of

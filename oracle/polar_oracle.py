@@ -166,6 +166,25 @@ def _f64(a, b):
     return np.sign(a) * np.sign(b) * np.minimum(np.abs(a), np.abs(b))
 
 
+def _f64_boxplus(a, b, jitter=None):
+    """my_sn/fec/polar/dec.py:331-340 (_cn_op_np): clip to +-30, log(1+exp(x+y)) - log(exp(x)+exp(y)), same operation order.
+    `jitter`: see _softplus_neg -- every exp / log result moved by -2 .. +2 ulp at random (numpy vs CUDA vs glibc)."""
+    x = np.maximum(np.minimum(a, LLR_MAX), -LLR_MAX)
+    y = np.maximum(np.minimum(b, LLR_MAX), -LLR_MAX)
+
+    def j(v):
+        if jitter is None:
+            return v
+        d = jitter.integers(-2, 3, size=np.shape(v))
+        for _ in range(2):
+            v = np.where(d > 0, np.nextafter(v, np.inf), np.where(d < 0, np.nextafter(v, -np.inf), v))
+            d = d - np.sign(d)
+        return v
+    out = j(np.log(1 + j(np.exp(x + y))))
+    out = out - j(np.log(j(np.exp(x)) + j(np.exp(y))))
+    return out
+
+
 def _g64(a, b, u):
     """polar_scl.py:107-108."""
     return np.multiply((1 - 2 * u), a) + b
@@ -183,7 +202,8 @@ def _softplus_neg(x, use_log1p=False, jitter=None):
     return v
 
 
-def scl_decode_full(logits, frozen, list_size, use_log1p=False, stable_sort=True, ulp_jitter_seed=None):
+def scl_decode_full(logits, frozen, list_size, use_log1p=False, stable_sort=True, ulp_jitter_seed=None, boxplus=False,
+                    fast_nodes=0):
     """Equivalent L-survivor formulation of polar_scl.py:121-209 (bit-exact incl. PMs):
     L paths with pm = [0, 30, ..., 30] (polar_scl.py:192-194; the reference's 2L slots are these L
     paths duplicated pairwise); frozen leaf: pm += softplus(-llr) (u=0); info leaf: fork every path
@@ -192,6 +212,11 @@ def scl_decode_full(logits, frozen, list_size, use_log1p=False, stable_sort=True
     `use_log1p` / `stable_sort` / `ulp_jitter_seed` give the oracle *variants* used to detect ill-conditioned
     lists."""
     jit = None if ulp_jitter_seed is None else np.random.default_rng(ulp_jitter_seed)
+    # boxplus=True: the Sionna-style list decoder my_sn/fec/polar/dec.py:158-537 with use_fast_scl=False (same recursion,
+    # exact boxplus check node); SECONDARY oracle (statistical parity: its exp / log are the host's)
+    fnode = (lambda a, b: _f64_boxplus(a, b, jit)) if boxplus else _f64
+    # fast_nodes = N > 0: the reference's use_fast_scl=True shortcuts (dec.py:269-306, 354-376) for rate-0 / REP nodes of up
+    # to N leaves (the reference itself has no size limit; the CUDA kernel prunes up to 32)
     llr_ch = (np.float32(-1.0) * np.asarray(logits, dtype=np.float32)).astype(np.float64)
     B, n = llr_ch.shape
     L = int(list_size)
@@ -232,9 +257,26 @@ def scl_decode_full(logits, frozen, list_size, use_log1p=False, stable_sort=True
             permute_all(par)
             state["u"][:, :, a] = bit
             return bit[:, :, None]
+        if fast_nodes and ln <= fast_nodes:
+            fr = frozen[a:a + ln]
+            xs = np.maximum(np.minimum(frame["L"], LLR_MAX), -LLR_MAX)
+            if fr.all():                                                         # dec.py:269-280 (rate-0)
+                state["pm"] = state["pm"] + _softplus_neg(xs, use_log1p, jit).sum(axis=-1)
+                return np.zeros((B, L, ln), dtype=np.uint8)
+            if fr[:-1].all() and not fr[-1]:                                     # dec.py:281-306 (REP)
+                c0 = state["pm"] + _softplus_neg(xs, use_log1p, jit).sum(axis=-1)
+                c1 = state["pm"] + _softplus_neg(-xs, use_log1p, jit).sum(axis=-1)
+                cand = np.concatenate([c0, c1], axis=1)
+                order = np.argsort(cand, axis=1, kind=kind)[:, :L]
+                par = order % L
+                bit = (order // L).astype(np.uint8)
+                state["pm"] = np.take_along_axis(cand, order, axis=1)
+                permute_all(par)
+                state["u"][:, :, a + ln - 1] = bit
+                return np.repeat(bit[:, :, None], ln, axis=2)
         h = ln // 2
         Lc = frame["L"]
-        left = {"L": _f64(Lc[:, :, :h], Lc[:, :, h:])}                           # polar_scl.py:134-137
+        left = {"L": fnode(Lc[:, :, :h], Lc[:, :, h:])}                          # polar_scl.py:134-137
         state["stack"].append(left)
         bl = rec(a, left)
         state["stack"].pop()

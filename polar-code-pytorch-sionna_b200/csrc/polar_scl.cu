@@ -53,6 +53,7 @@ struct SclParams {
   double *ws; size_t ws_doubles_per_warp; int s_glob;   // LLR stages >= s_glob live in ws
   size_t smem_per_warp;
   int words_global;                                     // scl2: partial-sum words live in ws (after the LLR stages)
+  int fast;                                             // boxplus build only: node-level path-metric updates (use_fast_scl)
 };
 
 // =====================================================================================================
@@ -106,9 +107,27 @@ __global__ void __launch_bounds__(128, SCL2_MINB) scl2_kernel(const SclParams P)
     unsigned long long rowL = idrow, rowB = idrow;
     uint32_t small = 0u, rootreg = 0u, fword = 0u;
 
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n;) {
       if ((i & 31) == 0) fword = __ldg(P.fmask + (i >> 5));
-      // ------------------------------------------------------------------ descent to leaf i
+      // Fast-SCL node shortcuts of the Sionna-style decoder (my_sn/fec/polar/dec.py:269-306, 354-376, use_fast_scl=True):
+      // a rate-0 node (all leaves frozen) or a REP node (only the last leaf carries information) of 2^s0 leaves is not
+      // descended into; its path-metric update is taken from the node's own stage-s0 LLRs.  Exact under the boxplus f
+      //  -- and only there, so the min-sum build never prunes.  Nodes up to 32 leaves (one mask word).
+      int sn = 0;                                               // stage of the pruned node (0: plain leaf)
+      bool rep = false;
+#if defined(POLAR_F_BOXPLUS)
+      if (P.fast) {
+        const int tmax = (i == 0) ? (m < 5 ? m : 5) : ((__ffs(i) - 1) < 5 ? (__ffs(i) - 1) : 5);
+        for (int s = tmax; s >= 1; --s) {
+          const uint32_t wbits = 1u << s;
+          const uint32_t full = (wbits == 32u) ? 0xFFFFFFFFu : ((1u << wbits) - 1u);
+          const uint32_t fm = (fword >> (i & 31)) & full;
+          if (fm == full) { sn = s; break; }
+          if (fm == (full >> 1)) { sn = s; rep = true; break; }
+        }
+      }
+#endif
+      // ------------------------------------------------------------------ descent to leaf i (to the node (s0, i) when pruning)
       int t;
       if (i == 0) {
         t = m;
@@ -153,7 +172,7 @@ __global__ void __launch_bounds__(128, SCL2_MINB) scl2_kernel(const SclParams P)
       }
       // f steps: stage s -> s-1 along left children (polar_scl.py:134-137); inputs are this path's own slot
       // (lane-private data from here on: no synchronisation needed)
-      for (int s = (t < m ? t : m); s >= 1; --s) {
+      for (int s = (t < m ? t : m); s >= sn + 1; --s) {
         const int h = 1 << (s - 1);
         double *dst = stage_ptr(s - 1) + lane;
         if (s == m) {
@@ -164,21 +183,40 @@ __global__ void __launch_bounds__(128, SCL2_MINB) scl2_kernel(const SclParams P)
           for (int e = 0; e < h; ++e) dst[e * 32] = f_minsum_d(src[e * 32], src[(e + h) * 32]);
         }
       }
-      {  // stages 0..min(t, m-1) were rewritten by this path into its own slot
+      {  // stages sn..min(t, m-1) were rewritten by this path into its own slot
         const int top = (t < m ? t : m - 1);
-        const unsigned long long msk = (top >= 11) ? 0x0FFFFFFFFFFFFFFFull : ((1ull << (5 * (top + 1))) - 1ull);
+        unsigned long long msk = (top >= 11) ? 0x0FFFFFFFFFFFFFFFull : ((1ull << (5 * (top + 1))) - 1ull);
+        if (sn > 0) msk &= ~((1ull << (5 * sn)) - 1ull);
         rowL = (rowL & ~msk) | (idrow & msk);
       }
-      // ------------------------------------------------------------------ leaf
-      double x = stage_ptr(0)[lane];
-      x = fmax(fmin(x, kLlrMaxD), -kLlrMaxD);                    // polar_scl.py:81
+      // ------------------------------------------------------------------ leaf (or pruned node)
       unsigned bit = 0u;
-      if ((fword >> (i & 31)) & 1u) {
-        pm += pm_penalty(x, 0u);                                   // frozen: u = 0
+      bool fork = false;
+      double k0, k1;
+      if (sn > 0) {
+        // dec.py:269-280 (rate-0): pm += sum_j log(1+exp(-llr_j)); dec.py:281-306 (REP): the same sum for the u = 0
+        // branch, the sum with the LLR signs flipped for the u = 1 branch, then sort and keep L
+        const double *node = stage_ptr(sn) + lane;
+        double a0 = 0.0, a1 = 0.0;
+        for (int e = 0; e < (1 << sn); ++e) {
+          const double xe = fmax(fmin(node[e * 32], kLlrMaxD), -kLlrMaxD);
+          a0 += pm_penalty(xe, 0u);
+          if (rep) a1 += pm_penalty(xe, 1u);
+        }
+        if (rep) { fork = true; k0 = pm + a0; k1 = pm + a1; }
+        else pm += a0;
       } else {
+        double x = stage_ptr(0)[lane];
+        x = fmax(fmin(x, kLlrMaxD), -kLlrMaxD);                  // polar_scl.py:81
+        if ((fword >> (i & 31)) & 1u) {
+          pm += pm_penalty(x, 0u);                                 // frozen: u = 0
+        } else {
+          fork = true; k0 = pm + pm_penalty(x, 0u); k1 = pm + pm_penalty(x, 1u);
+        }
+      }
+      if (fork) {
         // fork: candidate E = u*L + p  (reference slot order [u=0 paths | u=1 paths], polar_scl.py:49-68);
         // two candidates per lane, bitonic sort of the 2L candidates of each codeword inside its lane group
-        double k0 = pm + pm_penalty(x, 0u), k1 = pm + pm_penalty(x, 1u);
         int s0 = p, s1 = L + p;
 #pragma unroll
         for (int k = 2; k <= 2 * L; k <<= 1) {
@@ -209,11 +247,13 @@ __global__ void __launch_bounds__(128, SCL2_MINB) scl2_kernel(const SclParams P)
       }
       __syncwarp();   // forked paths read their parents' slots from here on
       // ------------------------------------------------------------------ partial-sum cascade
-      // z = number of completed right children above leaf i  (polar_scl.py:147-153, [bl ^ br, br])
-      const int z = (i == n - 1) ? m : (__ffs(~i) - 1);
-      uint32_t cur = bit;
+      // z = number of completed right children above the node that just finished -- leaf i, or the pruned node of 2^sn
+      // leaves whose partial sums are all `bit` (rate-0: 0; REP: x_hat = u.(1,...,1))  (polar_scl.py:147-153, [bl ^ br, br])
+      const int iend = i + (1 << sn) - 1;
+      const int z = (iend == n - 1) ? m : (__ffs(~iend) - 1);
+      uint32_t cur = (sn == 0) ? bit : (bit ? ((sn == 5) ? 0xFFFFFFFFu : ((1u << (1u << sn)) - 1u)) : 0u);
       const int zs = z < 5 ? z : 5;
-      for (int s = 0; s < zs; ++s) {
+      for (int s = sn; s < zs; ++s) {
         const uint32_t w = 1u << s;
         const uint32_t field = (small >> (w - 1u)) & ((1u << w) - 1u);
         cur = (field ^ cur) | (cur << w);
@@ -237,6 +277,7 @@ __global__ void __launch_bounds__(128, SCL2_MINB) scl2_kernel(const SclParams P)
         if (z < m) rowB = (rowB & ~(31ull << (5 * z))) | ((unsigned long long)p << (5 * z));
         __syncwarp();
       }
+      i = iend + 1;
     }  // leaves
 
     // ---------------------------------------------------------------------- epilogue
@@ -371,7 +412,8 @@ extern "C" size_t polar_scl_workspace_bytes(int n, int L, int64_t B) {
   if (!is_pow2(n) || n < 2 || n > POLAR_SCL_MAX_N || !is_pow2(L) || L > POLAR_SCL_MAX_L || B <= 0) return 0;
   const SclPlan pl = scl_plan(n, L, B);
   size_t need = (size_t)pl.grid * pl.warps_per_cta * pl.ws_doubles_per_warp * sizeof(double);
-#if !defined(POLAR_F_BOXPLUS)
+#if !defined(POLAR_F_BOXPLUS)      // the boxplus build has no scl3 (its compile time with exp/log inlined ~70 times per
+                                   // instantiation is 19 minutes); boxplus list decoding is scl2 with node pruning
   if (scl_mode() == 2 && scl3_supported(n, L)) {
     // scl3 is what runs; rows that are not 16-byte aligned fall back to scl2, which shrinks its grid to the workspace it
     // is given (at least one CTA per SM), so its much larger default appetite (1.3 GB at n=1024, L=8) is not reserved
@@ -387,10 +429,10 @@ extern "C" size_t polar_scl_workspace_bytes(int n, int L, int64_t B) {
   return need;
 }
 
-extern "C" int polar_scl_decode(const float *d_logit, const uint32_t *d_frozen_mask, int n, int L, int64_t B,
-                                uint32_t *d_best_packed, float *d_u_info_f32, const int32_t *d_info_pos, int k,
-                                double *d_pm_sorted, uint32_t *d_list_packed, const uint32_t *d_crc_rows, int crc_len,
-                                void *d_workspace, size_t workspace_bytes, void *stream) {
+static int scl_decode_impl(const float *d_logit, const uint32_t *d_frozen_mask, int n, int L, int64_t B,
+                           uint32_t *d_best_packed, float *d_u_info_f32, const int32_t *d_info_pos, int k,
+                           double *d_pm_sorted, uint32_t *d_list_packed, const uint32_t *d_crc_rows, int crc_len,
+                           void *d_workspace, size_t workspace_bytes, void *stream, int fast) {
   if (!is_pow2(n) || n < 2 || n > POLAR_SCL_MAX_N) return set_error(POLAR_EINVAL, "scl: n=%d must be a power of two in [2,%d]", n, POLAR_SCL_MAX_N);
   if (!is_pow2(L) || L > POLAR_SCL_MAX_L) return set_error(POLAR_EINVAL, "scl: list_size=%d must be a power of two <= %d", L, POLAR_SCL_MAX_L);
   if (B < 0) return set_error(POLAR_EINVAL, "scl: B < 0");
@@ -401,7 +443,7 @@ extern "C" int polar_scl_decode(const float *d_logit, const uint32_t *d_frozen_m
   if (crc_len < 0 || crc_len > 32 || (crc_len > 0 && !d_crc_rows)) return set_error(POLAR_EINVAL, "scl: bad crc_len / crc_rows");
   if (crc_len > 0 && (k < 1 || k > n)) return set_error(POLAR_EINVAL, "scl: CRC-aided selection needs k (penalty 30 k, dec.py:517-518), got k=%d", k);
 #if !defined(POLAR_F_BOXPLUS)
-  if (scl_mode() == 2 && scl3_supported(n, L) && ((uintptr_t)d_logit & 15) == 0) {
+  if (!fast && scl_mode() == 2 && scl3_supported(n, L) && ((uintptr_t)d_logit & 15) == 0) {
     Scl3Plan p3;
     int rc = launch_scl3(d_logit, d_frozen_mask, n, L, B, d_best_packed, d_u_info_f32, d_info_pos, k, d_pm_sorted, d_list_packed,
                          d_crc_rows, crc_len, d_workspace, (cudaStream_t)stream, &p3);
@@ -430,7 +472,7 @@ extern "C" int polar_scl_decode(const float *d_logit, const uint32_t *d_frozen_m
   P.best = d_best_packed; P.u_info = d_u_info_f32; P.info_pos = d_info_pos; P.k = k;
   P.pm_out = d_pm_sorted; P.list = d_list_packed; P.crc_rows = d_crc_rows; P.crc_len = crc_len;
   P.ws = (double *)d_workspace; P.ws_doubles_per_warp = pl.ws_doubles_per_warp; P.s_glob = pl.s_glob;
-  P.smem_per_warp = pl.smem_per_warp; P.words_global = pl.words_global;
+  P.smem_per_warp = pl.smem_per_warp; P.words_global = pl.words_global; P.fast = fast;
   cudaStream_t st = (cudaStream_t)stream;
   switch (L) {
     case 1: return launch_scl<1>(P, pl, st);
@@ -441,3 +483,21 @@ extern "C" int polar_scl_decode(const float *d_logit, const uint32_t *d_frozen_m
     default: return launch_scl<32>(P, pl, st);
   }
 }
+
+extern "C" int polar_scl_decode(const float *d_logit, const uint32_t *d_frozen_mask, int n, int L, int64_t B,
+                                uint32_t *d_best_packed, float *d_u_info_f32, const int32_t *d_info_pos, int k,
+                                double *d_pm_sorted, uint32_t *d_list_packed, const uint32_t *d_crc_rows, int crc_len,
+                                void *d_workspace, size_t workspace_bytes, void *stream) {
+  return scl_decode_impl(d_logit, d_frozen_mask, n, L, B, d_best_packed, d_u_info_f32, d_info_pos, k, d_pm_sorted, d_list_packed,
+                         d_crc_rows, crc_len, d_workspace, workspace_bytes, stream, 0);
+}
+#if defined(POLAR_F_BOXPLUS)
+// use_fast_scl = True of the Sionna-style decoder: rate-0 / REP nodes update the path metric at node level
+extern "C" int polar_scl_decode_boxplus_pruned(const float *d_logit, const uint32_t *d_frozen_mask, int n, int L, int64_t B,
+                                               uint32_t *d_best_packed, float *d_u_info_f32, const int32_t *d_info_pos, int k,
+                                               double *d_pm_sorted, uint32_t *d_list_packed, const uint32_t *d_crc_rows, int crc_len,
+                                               void *d_workspace, size_t workspace_bytes, void *stream) {
+  return scl_decode_impl(d_logit, d_frozen_mask, n, L, B, d_best_packed, d_u_info_f32, d_info_pos, k, d_pm_sorted, d_list_packed,
+                         d_crc_rows, crc_len, d_workspace, workspace_bytes, stream, 1);
+}
+#endif

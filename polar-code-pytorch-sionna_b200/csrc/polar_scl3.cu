@@ -55,6 +55,15 @@ struct Params {
 };
 
 // ---- f / g on fp32 (exact for f) and fp64 ----------------------------------------------------------
+#if defined(POLAR_F_BOXPLUS)
+// exact boxplus of the Sionna-style list decoder (my_sn/fec/polar/dec.py:331-340, numpy float64): clip to +-30,
+// ln(1+e^(x+y)) - ln(e^x+e^y), always in fp64 (polar_bp_wrap.cu compiles this unit a second time into namespace polar_bp)
+PDEV double fop(double a, double b) {
+  const double x = fmax(fmin(a, kLlrMaxD), -kLlrMaxD), y = fmax(fmin(b, kLlrMaxD), -kLlrMaxD);
+  return log(1.0 + exp(x + y)) - log(exp(x) + exp(y));
+}
+PDEV double fop(float a, float b) { return fop((double)a, (double)b); }
+#else
 PDEV float fop(float a, float b) {          // polar_scl.py:93-106 on fp32-representable values: exact
   const float mag = fminf(fminf(fabsf(a), fabsf(b)), 30.0f);
   return __uint_as_float(__float_as_uint(mag) | ((__float_as_uint(a) ^ __float_as_uint(b)) & 0x80000000u));
@@ -66,6 +75,7 @@ PDEV double fop(double a, double b) {
   const int hi = (__double2hiint(a) ^ __double2hiint(b)) & 0x80000000;
   return __hiloint2double(__double2hiint(mag) | hi, __double2loint(mag));
 }
+#endif
 PDEV double gop(double a, double b, unsigned u) {   // polar_scl.py:107-108; u in {0,1}
   const double sa = __hiloint2double(__double2hiint(a) ^ (int)(u << 31), __double2loint(a));
   return __dadd_rn(sa, b);
@@ -653,6 +663,7 @@ int launch_scl3(const float *logit, const uint32_t *fmask, int n, int L, int64_t
 
 }  // namespace polar
 
+#if !defined(POLAR_F_BOXPLUS)
 // Debug / test hook (not part of include/polar_b200.h): d_mismatch[3] += number of arguments (of `count` pseudo-random
 // ones in [-30, 30]) on which exp_nb / log_nb / softplus_literal differ bitwise from the CUDA math library.
 extern "C" int polar_scl3_math_selftest(uint64_t count, unsigned long long *d_mismatch, void *stream) {
@@ -662,3 +673,4 @@ extern "C" int polar_scl3_math_selftest(uint64_t count, unsigned long long *d_mi
   POLAR_CHECK_LAUNCH("math_selftest_kernel");
   return POLAR_OK;
 }
+#endif

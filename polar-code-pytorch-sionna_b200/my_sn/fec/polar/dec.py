@@ -1,9 +1,8 @@
-"""my_sn decoders (my_sn/fec/polar/dec.py).  Built this round: the CRC-aided SCL decoder
-(dec.py:158-537, selection logic :507-527) on the min-sum list kernel -- the composed oracle of
-SURVEY 8(c) for BASELINE config 3.  `SC_Dec` below is the Sionna-style boxplus SC decoder
-(dec.py:13-157).  The reference's my_sn SCL variant also evaluates f with the exact boxplus and prunes
-rate-0/REP nodes; that part of N2 is not built (documented in DESIGN.md); `use_fast_scl` / `use_hybrid_sc` are accepted
-and ignored like dec.py:237-238."""
+"""my_sn decoders (my_sn/fec/polar/dec.py): the CRC-aided SCL decoder (dec.py:158-537, selection logic :507-527) --
+on the min-sum list kernel it is the composed oracle of SURVEY 8(c) for BASELINE config 3 -- and the Sionna-style boxplus
+SC / SCL decoders (dec.py:13-157 / :158-537).  `use_fast_scl=True` (the default) runs the list kernel
+with the reference's rate-0 / REP node shortcuts (dec.py:269-306, 354-376: node-level path-metric updates, the subtree
+is not descended into); `use_hybrid_sc` is accepted and ignored like dec.py:237-238."""
 import numpy as np
 import torch as tc
 from torch import nn
@@ -51,9 +50,10 @@ class SC_Dec(nn.Module):
 
 class SCL_Dec(nn.Module):
   """Sionna-style list decoder (my_sn/fec/polar/dec.py:158-537) with CRC-aided selection (:507-527).
-  cn_type="boxplus" (default, the reference's arithmetic): exact boxplus f in fp64 with leaf-level path-metric updates,
-  i.e. the reference with use_fast_scl=False; its default rate-0/REP node shortcuts only change how the same penalties
-  are accumulated, so `use_fast_scl` is accepted and both settings run this kernel (statistical parity).
+  cn_type="boxplus" (default, the reference's arithmetic): exact boxplus f in fp64; `use_fast_scl=True` (default) takes the
+  path-metric update of rate-0 / REP nodes of up to 32 leaves from the node's own LLRs and skips the subtree
+  (`polar_scl_decode_boxplus_pruned`), `use_fast_scl=False` updates leaf by leaf (`polar_scl_decode_boxplus`).  Parity
+  with the CPU reference is statistical for both (its exp / log are the host's).
   cn_type="minsum": the x_run min-sum list kernel under the same CRC-aided selection -- the composed oracle of
   BASELINE config 3, bit-exact against `tests/golden/sclcrc_*`."""
 
@@ -63,6 +63,7 @@ class SCL_Dec(nn.Module):
     self.device = device
     assert cn_type in ("boxplus", "minsum"), "cn_type must be 'boxplus' or 'minsum'."
     self._boxplus = cn_type == "boxplus"
+    self._pruned = bool(use_fast_scl) and self._boxplus
     if output_dtype not in (tc.float16, tc.float32, tc.float64):
       raise ValueError('output_dtype must be {tf.float16, tf.float32, tf.float64}.')
     self.output_dtype = output_dtype
@@ -120,7 +121,7 @@ class SCL_Dec(nn.Module):
     """Device fast path of the on-device Monte-Carlo loop: bit-packed decisions of the (CRC-)selected path."""
     rows, ln = self._rows_on(tables.dev)
     return dk.scl_decode(logits, tables, self._list_size, crc_rows=rows, crc_len=ln, want_info=False,
-                         want_packed=True, boxplus=self._boxplus, out_packed=out)["u_packed"]
+                         want_packed=True, boxplus=self._boxplus, out_packed=out, pruned=self._pruned)["u_packed"]
 
   def forward(self, inputs):
     assert inputs.dtype == self.output_dtype, "Invalid input dtype."
@@ -139,7 +140,7 @@ class SCL_Dec(nn.Module):
                                                crc_rows_np=self._crc_rows_np if self._use_crc else None, crc_len=ln)
     else:
       res = dk.scl_decode(inputs, tables, self._list_size, crc_rows=rows, crc_len=ln, want_info=True, want_pm=True,
-                          boxplus=self._boxplus)
+                          boxplus=self._boxplus, pruned=self._pruned)
       u_info, self.msg_pm = res["u_info"], res["pm"]
     output_shape = list(inputs.shape)
     output_shape[-1] = self.k

@@ -56,6 +56,7 @@ _SIGNATURES = {
   "polar_scl_decode": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
   "polar_scl_boxplus_workspace_bytes": (_sz, [_i32, _i32, _i64]),
   "polar_scl_decode_boxplus": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
+  "polar_scl_decode_boxplus_pruned": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
   "polar_encode_packed": (_i32, [_vp, _i32, _i64, _vp, _vp]),
   "polar_encode_f32": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp]),
   "polar_gather_cols_f32": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp]),
@@ -234,7 +235,7 @@ _WS_CACHE = {}
 
 
 def scl_decode(logits, tables, list_size, crc_rows=None, crc_len=0, want_info=True, want_packed=False,
-               want_pm=False, want_list=False, boxplus=False, out_packed=None):
+               want_pm=False, want_list=False, boxplus=False, out_packed=None, pruned=False):
   """polar_scl_decode (min-sum f) or polar_scl_decode_boxplus (exact boxplus f, my_sn SCL_Dec)
   -> dict(u_info, u_packed, pm [B,L] fp64, list [B,L,words] int32)."""
   dev = tables.dev
@@ -253,7 +254,8 @@ def scl_decode(logits, tables, list_size, crc_rows=None, crc_len=0, want_info=Tr
     out["list"] = tc.empty((B, L, words(n)), dtype=tc.int32, device=dev)
   with tc.cuda.device(dev):
     fn_ws = lib().polar_scl_boxplus_workspace_bytes if boxplus else lib().polar_scl_workspace_bytes
-    fn_dec = lib().polar_scl_decode_boxplus if boxplus else lib().polar_scl_decode
+    fn_dec = lib().polar_scl_decode if not boxplus else (
+      lib().polar_scl_decode_boxplus_pruned if pruned else lib().polar_scl_decode_boxplus)   # pruned: use_fast_scl node shortcuts
     need = int(fn_ws(n, L, B)) if B > 0 else 0
     ws = None
     if need:
