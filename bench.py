@@ -198,15 +198,21 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------
-def source_stamp():
-    """sha1 over the kernel sources: ncu-derived constants (instructions per codeword, DRAM bytes per launch) are only
-    valid for the sources they were captured from (profiles/sc_counters.json carries the stamp of its capture)."""
+KERNEL_SOURCES = {
+    # files a kernel's translation unit is built from (csrc/Makefile): a capture is valid while these are unchanged
+    "sc5_kernel<10>": ("polar_sc5.cu", "polar_common.cuh", "polar_warp.cuh", "polar_internal.h"),
+    "scl3_kernel<10,8>": ("polar_scl3.cu", "polar_softplus.cuh", "polar_common.cuh", "polar_warp.cuh", "polar_internal.h"),
+}
+
+
+def source_stamp(kernel_key):
+    """sha1 over the sources of one kernel: ncu-derived constants (instructions per codeword, DRAM bytes per launch) are
+    only valid for the sources they were captured from (profiles/sc_counters.json carries the stamp of each capture)."""
     import hashlib
     h = hashlib.sha1()
     d = os.path.join(PKG, "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh", ".h")):
-            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    for f in KERNEL_SOURCES[kernel_key]:
+        h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 
 
@@ -215,10 +221,12 @@ def ncu_counters(kernel_key):
     p = os.path.join(ROOT, "profiles", "sc_counters.json")
     if not os.path.exists(p):
         return None, "no capture"
-    d = json.load(open(p))
-    if d.get("source_stamp") != source_stamp():
-        return None, "stale: captured for sources %s, current %s" % (d.get("source_stamp"), source_stamp())
-    return d.get(kernel_key), "ncu capture of these sources (profiles/sc_counters.json)"
+    d = json.load(open(p)).get(kernel_key)
+    if not d:
+        return None, "no capture"
+    if d.get("source_stamp") != source_stamp(kernel_key):
+        return None, "stale: captured for sources %s, current %s" % (d.get("source_stamp"), source_stamp(kernel_key))
+    return d, "ncu capture of these sources (profiles/sc_counters.json)"
 
 
 def run_sweep(kind, world, dev, sampler, barrier, max_over_ranks):

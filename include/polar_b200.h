@@ -194,6 +194,19 @@ int polar_count_errors_f32(const float *d_b, const float *d_b_hat, int k, int64_
 int polar_mc_control(unsigned long long *d_delta4, long long *d_state8, long long target_bit_errs,
                      long long target_block_errs, long long max_mc_iter, void *stream);
 
+/* ---- N4: ordered-statistics decoder (my_sn/fec/osd/dec.py:8-192, OSDecoder.forward :149-191) -------------------
+ * One CTA per codeword: reliability sort, most-reliable basis by the reference's pivot method (:99-117), hard decisions
+ * on the pivots re-encoded, every error pattern of weight 1..t in itertools.combinations order (:57-62) under the
+ * LLR distance mean log(1 + exp(llr (1 - 2c))) (:64-79, fp32), first minimum within a weight, strictly smaller across
+ * weights (:181-184).  Decisions equal the reference's except where two candidates are closer than fp32 rounding.
+ *  d_gm_rows   generator matrix, bit-packed rows [k, (n+31)/32] in the ORIGINAL column order (dec.py:40-42)
+ *  d_c_packed  [B, (n+31)/32] decided codeword bits (all n positions, like the reference) or NULL
+ *  d_c_f32     [B, n] the same as fp32 0./1. (what OSDecoder.forward returns) or NULL (one of the two is required)
+ *  d_dist      [B] distance of the decided codeword, or NULL
+ *  2 <= n <= 1024, 1 <= k <= n, 0 <= t <= 6, C(k, t) < 2^31. */
+int polar_osd_decode(const float *d_logit, const uint32_t *d_gm_rows, int n, int k, int t, int64_t B,
+                     uint32_t *d_c_packed, float *d_c_f32, float *d_dist, void *stream);
+
 /* Test hook: d_mismatch3[0..2] += how many of `count` pseudo-random arguments in [-30, 30] make the decoder's own
  * exp / log / log(1+exp(.)) sequences (csrc/polar_softplus.cuh) differ BITWISE from the CUDA math library's. */
 int polar_scl3_math_selftest(uint64_t count, unsigned long long *d_mismatch3, void *stream);

@@ -181,6 +181,37 @@ def gen_scl_boxplus(fz):
              bits=bits.astype(np.uint8), crc_degree=np.array(crc if crc else ""), list_size=np.int64(L))
 
 
+def gen_osd(fz):
+    """the reference's OSDecoder (my_sn/fec/osd/dec.py:8-192) on polar codes (its G = the encoder applied
+    to the identity, dec.py:40-42).  The numpy restatement must return the reference's codewords."""
+    from my_sn.fec.osd.dec import OSDecoder
+    out = {}
+    for (n, k, t, bs, no) in ((16, 8, 3, 120, 0.8), (32, 16, 2, 160, 0.6), (64, 32, 1, 160, 0.7), (64, 32, 2, 48, 0.7),
+                              (128, 64, 1, 48, 0.8), (128, 100, 0, 64, 0.3)):
+        fp = fz["rm_%d_%d" % (n, k)] if "rm_%d_%d" % (n, k) in fz else po.rm_frozen_pos(n, n - k)
+        enc = MyEnc(fp, n)
+        dec = OSDecoder(t=t, encoder=enc)
+        set_seed(1700 + n + t)
+        u = tc.randint(0, 2, (bs, k)).float()
+        c = enc(u)
+        y = (1 - 2 * c) + tc.randn(bs, n) * float(np.sqrt(no))
+        logit = (-2 * y / no).float()
+        # row 0: |llr| up to 95 -- exp() overflows to inf in fp32 above 88.7, so wrong decisions there cost inf (dec.py:78).
+        # (Magnitudes at the +-100 clip would tie, and torch.argsort leaves the order of ties open.)
+        logit[0] = logit[0] * (95.0 / float(logit[0].abs().max()))
+        c_ref = dec(logit).numpy().astype(np.uint8)
+        gm = dec._gm.numpy().astype(np.uint8)
+        got, d, gap = po.osd_decode(logit.numpy(), gm, t)
+        bad = (got != c_ref).any(axis=1)
+        print("osd n=%d k=%d t=%d: BLER %.3f, restatement differs on %d of %d (smallest candidate gap %.2e)" %
+              (n, k, t, float((c_ref != c.numpy()).any(axis=1).mean()), int(bad.sum()), bs, gap.min()))
+        assert not bad.any()
+        key = "%d_%d_t%d" % (n, k, t)
+        out["logits_" + key] = logit.numpy(); out["gm_" + key] = gm; out["c_hat_" + key] = c_ref
+        out["c_tx_" + key] = c.numpy().astype(np.uint8); out["gap_" + key] = gap
+    save("osd", **out)
+
+
 def gen_5g():
     """5G rate matching (my_sn/fec/polar/enc.py:115-392) and rate recovery (dec.py:539-667) of the reference:
     index plans, encoded codewords and de-rate-matched decoder inputs for puncturing, shortening and repetition."""
@@ -391,7 +422,7 @@ def gen_readme_kat(fz):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["frozen", "enc", "sc", "scbp", "nr5g", "sclbp", "scl", "crc", "frontend", "readme"]
+    which = sys.argv[1:] or ["frozen", "enc", "sc", "scbp", "nr5g", "sclbp", "scl", "crc", "frontend", "readme", "osd"]
     fz = gen_frozen() if "frozen" in which else dict(np.load(os.path.join(OUT, "frozen_sets.npz")))
     if "enc" in which:
         gen_enc(fz)
@@ -411,3 +442,5 @@ if __name__ == "__main__":
         gen_scl_boxplus(fz)
     if "scl" in which:
         gen_scl(fz)
+    if "osd" in which:
+        gen_osd(fz)

@@ -423,3 +423,69 @@ def count_errors(b, b_hat):
 
 def count_block_errors(b, b_hat):
     return int(np.sum(np.any(np.asarray(b) != np.asarray(b_hat), axis=-1)))
+
+
+# ------------------------------------------------------------------------------------------------
+# N4  ordered-statistics decoder       my_sn/fec/osd/dec.py:8-192
+# ------------------------------------------------------------------------------------------------
+def osd_decode(logits, gm, t, dtype=np.float32):
+    """Restatement of OSDecoder.forward (dec.py:149-191) for a generator matrix gm [k, n] of 0/1.
+    Steps (same order as the reference): clip to +-100 (:155); positions by |llr| descending (:157; equal magnitudes in
+    index order -- torch.argsort leaves that open); most-reliable basis by the pivot method (:99-117: row c's pivot =
+    its first set column, cleared from every other row); second permutation to [pivots | remaining columns ascending]
+    (:118-134); hard decisions llr > 0 on the pivots, re-encoded (:171-174); distance mean_j log(1 + exp(llr_j (1 - 2c_j)))
+    (:64-79) in `dtype`; error patterns itertools.combinations(range(k), w) for w = 1 .. t (:57-62), argmin (first) within
+    a weight (:93), strictly smaller across weights (:181-184); inverse permutation (:186-188).
+    Returns (c_hat uint8 [B, n], distance [B], gap [B]) where gap = (runner-up distance - winning distance) / winning
+    distance over ALL tested candidates, computed in float64: a decision whose gap is at rounding level is one the
+    reference itself does not reproduce across exp/log/sum implementations."""
+    import itertools
+    x = np.clip(np.asarray(logits, dtype=np.float32), -100.0, 100.0)
+    gm = (np.asarray(gm) != 0).astype(np.uint8)
+    k, n = gm.shape
+    B = x.shape[0]
+    pats = [np.array(list(itertools.combinations(range(k), w)), dtype=np.int64).reshape(-1, w) for w in range(1, t + 1) if w <= k]
+    out = np.zeros((B, n), dtype=np.uint8)
+    dist = np.zeros(B, dtype=dtype)
+    gap = np.zeros(B, dtype=np.float64)
+    for b in range(B):
+        order = np.argsort(-np.abs(x[b]), kind="stable")
+        g = gm[:, order].copy()
+        piv = []
+        for c in range(k):
+            p = int(np.argmax(g[c]))
+            piv.append(p)
+            hit = g[:, p].astype(bool)
+            hit[c] = False
+            g[hit] ^= g[c]
+        rest = [j for j in range(n) if j not in set(piv)]
+        perm2 = np.array(piv + rest, dtype=np.int64)
+        g = g[:, perm2]
+        order = order[perm2]
+        l = x[b, order]
+
+        def distance(cands, dt):
+            ll = l.astype(dt)[None, :] * (dt(1) - dt(2) * cands.astype(dt))
+            with np.errstate(over="ignore"):
+                return np.mean(np.log(dt(1) + np.exp(ll)), axis=1, dtype=dt)
+
+        u = (l[:k] > 0).astype(np.uint8)
+        c0 = (u.astype(np.int64) @ g.astype(np.int64) % 2).astype(np.uint8)
+        best_c, best_d = c0, distance(c0[None], dtype)[0]
+        all_d = [distance(c0[None], np.float64)]
+        for ep in pats:
+            e = np.zeros((ep.shape[0], n), dtype=np.uint8)
+            for col in range(ep.shape[1]):
+                e ^= g[ep[:, col]]
+            cand = e ^ c0[None, :]
+            d = distance(cand, dtype)
+            i = int(np.argmin(d))
+            if d[i] < best_d:
+                best_d, best_c = d[i], cand[i]
+            all_d.append(distance(cand, np.float64))
+        all_d = np.sort(np.concatenate(all_d))
+        gap[b] = (all_d[1] - all_d[0]) / max(all_d[0], 1e-300) if all_d.size > 1 and np.isfinite(all_d[1]) else np.inf
+        inv = np.argsort(order)
+        out[b] = best_c[inv]
+        dist[b] = best_d
+    return out, dist, gap

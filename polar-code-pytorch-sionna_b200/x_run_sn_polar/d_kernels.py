@@ -68,6 +68,7 @@ _SIGNATURES = {
   "polar_count_errors_packed": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
   "polar_count_errors_f32": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp]),
   "polar_mc_control": (_i32, [_vp, _vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _vp]),
+  "polar_osd_decode": (_i32, [_vp, _vp, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp]),
   "polar_scl3_math_selftest": (_i32, [ctypes.c_uint64, _vp, _vp]),
   "polar_pack_bits_f32": (_i32, [_vp, _i32, _i64, _vp, _vp]),
   "polar_unpack_info_f32": (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _vp]),
@@ -440,6 +441,31 @@ def mc_control(delta, state, target_bit_errs, target_block_errs, max_mc_iter):
   tk = -1 if target_block_errs is None else int(target_block_errs)
   with tc.cuda.device(dev):
     check(lib().polar_mc_control(ptr(delta), ptr(state), tb, tk, int(max_mc_iter), stream_ptr(dev)))
+
+
+def pack_rows(m):
+  """0/1 matrix [r, n] (numpy) -> uint32 bit-packed rows [r, (n+31)//32], position i = bit i%32 of word i//32 (as int32)."""
+  m = (np.asarray(m) != 0).astype(np.uint8)
+  r, n = m.shape
+  nw = (n + 31) // 32
+  pad = np.zeros((r, nw * 32), dtype=np.uint8)
+  pad[:, :n] = m
+  return np.packbits(pad.reshape(r, nw, 32), axis=2, bitorder="little").view(np.uint32).reshape(r, nw).view(np.int32).copy()
+
+
+def osd_decode(logits, gm_rows, n, k, t, want_f32=True, want_packed=False, want_dist=False):
+  """polar_osd_decode: logits [B,n] + bit-packed generator rows (device int32 [k, words]) -> dict(c fp32 [B,n], c_packed, dist)."""
+  dev = gm_rows.device
+  x = _prep_logits(logits, n, dev)
+  B = x.shape[0]
+  nw = (n + 31) // 32
+  out = {"c": tc.empty((B, n), dtype=tc.float32, device=dev) if want_f32 else None,
+         "c_packed": tc.empty((B, nw), dtype=tc.int32, device=dev) if want_packed else None,
+         "dist": tc.empty((B,), dtype=tc.float32, device=dev) if want_dist else None}
+  with tc.cuda.device(dev):
+    check(lib().polar_osd_decode(ptr(x), ptr(gm_rows), n, k, int(t), B, ptr(out["c_packed"]), ptr(out["c"]), ptr(out["dist"]),
+                                 stream_ptr(dev)))
+  return out
 
 
 def launch_count():

@@ -1,0 +1,10 @@
+#!/bin/bash
+# GPU box: full GPU suite, both bench arms, launch list, full ncu captures of the three headline kernels
+python -m pytest tests -m gpu -x -q > gpurun_out/r4a_tests.log 2>&1; tail -3 gpurun_out/r4a_tests.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/r4a_bench.json 2> gpurun_out/r4a_bench.err; echo bench rc=$?
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r4a_ref.json 2> gpurun_out/r4a_ref.err; echo ref rc=$?
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_bench_launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/r4a_ncu_bench.log 2>&1; echo ncu-list rc=$?
+for t in sc:sc5_kernel:r02_sc5_n1024 sc4096:sc5_kernel:r02_sc5_n4096 sc2048:sc5_kernel:r02_sc5_n2048 scl:scl3_kernel:r02_scl3; do
+  IFS=: read what kern out <<< "$t"
+  ncu --set full --clock-control none --import-source on -k regex:$kern -s 1 -c 1 -f -o gpurun_out/$out python tools/ncu_target.py $what 2 > gpurun_out/r4a_ncu_$what.log 2>&1; echo "ncu $what rc=$?"
+done

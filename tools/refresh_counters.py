@@ -16,7 +16,7 @@ from bench import source_stamp  # noqa: E402
 METRICS = "smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum"
 
 
-def capture(what, match, batch):
+def capture(key, what, match, batch):
     cmd = ["ncu", "--metrics", METRICS, "--clock-control", "none", "--csv", "-k", "regex:" + match, "-c", "2",
            sys.executable, os.path.join(ROOT, "tools", "ncu_target.py"), what, "2"]
     raw = subprocess.run(cmd, capture_output=True, text=True).stdout
@@ -27,17 +27,16 @@ def capture(what, match, batch):
     for r in rows[1:]:
         last.setdefault(r[iid], {"kernel": r[ik]})[r[im]] = float(r[iv].replace(",", ""))
     m = last[sorted(last, key=int)[-1]]                    # second (warm) launch
-    return {"kernel": m["kernel"], "batch": batch, "warp_instr_per_codeword": m["smsp__inst_executed.sum"] / batch,
+    return {"source_stamp": source_stamp(key), "kernel": m["kernel"], "batch": batch, "warp_instr_per_codeword": m["smsp__inst_executed.sum"] / batch,
             "dram_bytes_per_launch": m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"],
             "dram_bytes_read": m["dram__bytes_read.sum"], "dram_bytes_write": m["dram__bytes_write.sum"],
             "ncu_time_ms": m["gpu__time_duration.sum"] / 1e6}
 
 
 def main():
-    out = {"source_stamp": source_stamp(),
-           "how": "ncu --metrics %s --clock-control none (tools/refresh_counters.py), second launch" % METRICS,
-           "sc5_kernel<10>": capture("sc", "sc5_kernel", 1 << 20),
-           "scl3_kernel<10,8>": capture("scl", "scl3_kernel", 1 << 18)}
+    out = {"how": "ncu --metrics %s --clock-control none (tools/refresh_counters.py), second launch" % METRICS,
+           "sc5_kernel<10>": capture("sc5_kernel<10>", "sc", "sc5_kernel", 1 << 20),
+           "scl3_kernel<10,8>": capture("scl3_kernel<10,8>", "scl", "scl3_kernel", 1 << 18)}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "sc_counters.json"), "w"), indent=1)
     print(json.dumps(out, indent=1))
