@@ -37,14 +37,15 @@ __host__ __device__ inline OsdLayout osd_layout(int n, int k) {
   while (p < n) p <<= 1;
   l.np2 = p;
   size_t o = 0;
-  l.rows_off = o; o += (size_t)k * l.nw * 4;        // G, columns in sorted order, bit-packed rows
-  l.key_off = o; o += (size_t)l.np2 * 4;            // |llr| (sort keys); afterwards the clipped logits in sorted order
-  l.idx_off = o; o += (size_t)l.np2 * 4;            // original position of sorted position j
-  l.cost_off = o; o += (size_t)n * 8;               // {log(1+exp(+llr_j)), log(1+exp(-llr_j))}: cost of c_j = 0 / 1
-  l.vec_off = o; o += (size_t)3 * l.nw * 4;         // order-0 codeword, prefix candidate, output words
-  l.piv_off = o; o += (size_t)k * 4;
-  l.flag_off = o; o += (size_t)k * 4;
-  l.red_off = o; o += 256;
+  auto take = [&o](size_t bytes) { const size_t at = o; o += (bytes + 15) / 16 * 16; return at; };   // 16-byte aligned pieces
+  l.rows_off = take((size_t)k * l.nw * 4);         // G, columns in sorted order, bit-packed rows
+  l.key_off = take((size_t)l.np2 * 4);             // |llr| (sort keys); afterwards the clipped logits in sorted order
+  l.idx_off = take((size_t)l.np2 * 4);             // original position of sorted position j
+  l.cost_off = take((size_t)n * 8);                // {log(1+exp(+llr_j)), log(1+exp(-llr_j))}: cost of c_j = 0 / 1
+  l.vec_off = take((size_t)3 * l.nw * 4);          // order-0 codeword, prefix candidate, output words
+  l.piv_off = take((size_t)k * 4);
+  l.flag_off = take((size_t)k * 4);
+  l.red_off = take(256);
   l.total = (o + 15) / 16 * 16;
   return l;
 }

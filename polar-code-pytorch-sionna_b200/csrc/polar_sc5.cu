@@ -229,9 +229,7 @@ PDEV float4 tm_hi(const Tm8 &v) { return make_float4(u2f(v.r[4]), u2f(v.r[5]), u
 template <int D, bool FIRST_G, bool FROM_CH, int NS>
 __device__ __noinline__ void descent(const float *__restrict__ src, const int nvalid, const uint32_t *beta, const int nws,
                                      const int left_word, float *scr, const uint32_t tm_base, float *Lw, const uint32_t bar_a,
-                                     uint32_t &par, const int lane, const int discard_pol) {
-  const bool discard = (discard_pol & 1) != 0;
-  const int polsel = discard_pol >> 1;
+                                     uint32_t &par, const int lane, const bool discard) {
   constexpr int NB = 1 << D;                       // 256-column source blocks per codeword
   constexpr int HB = NB / 2;                       // blocks of the stage 8+D-1 node
   constexpr int SRC = 256 * NB;                    // floats per codeword in the source
@@ -242,16 +240,8 @@ __device__ __noinline__ void descent(const float *__restrict__ src, const int nv
   constexpr int T1 = 8 + D - 1;                    // stage of the node the first update produces
   // channel rows are streamed (nobody comes back within the L2's reach); a scratch node must stay in the L2 until the
   // discard that follows its only read -- reading it evict_first would get the dirty line written back before that
-  uint64_t pol_src = FROM_CH ? l2_policy_evict_first() : (D == 1 ? l2_policy_evict_last() : l2_policy_evict_normal());
-  uint64_t pol_s9 = l2_policy_evict_last();
-  const uint64_t pol_sx = l2_policy_evict_normal();
-  if (polsel) {       // tuning experiment (POLAR_SC5_POL = 100 row + 10 scratch read + scratch store; 1 last, 2 normal, 3 first)
-    const uint64_t pl[4] = {0, l2_policy_evict_last(), l2_policy_evict_normal(), l2_policy_evict_first()};
-    const int a = polsel % 10, b = (polsel / 10) % 10, c = (polsel / 100) % 10;
-    if (a) pol_s9 = pl[a & 3];
-    if (!FROM_CH && D == 1 && b) pol_src = pl[b & 3];
-    if (FROM_CH && c) pol_src = pl[c & 3];
-  }
+  const uint64_t pol_src = FROM_CH ? l2_policy_evict_first() : (D == 1 ? l2_policy_evict_last() : l2_policy_evict_normal());
+  const uint64_t pol_s9 = l2_policy_evict_last(), pol_sx = l2_policy_evict_normal();
   if (!FROM_CH) asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy scratch writes -> bulk-copy reads
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // the stage-7 buffer (generic writes) becomes staging space
   __syncwarp();
@@ -552,13 +542,13 @@ __global__ void __launch_bounds__(256, 1) sc5_kernel(const float *__restrict__ l
         const int S = (i == 0) ? M : 7 + (__ffs(i) - 1);
         const bool dead = __shfl_sync(FULLMASK, (int)(nz[i] & nz[i + 1]), 0) != 0;       // nobody will read this stage-8 node
         if (S == M) {
-          descent<M - 8, false, true, NS>(logit + cw0 * (int64_t)N, nvalid, beta, NWS, 0, scr, tm_base, L, bar_a, par, lane, scr_discard & ~1);
+          descent<M - 8, false, true, NS>(logit + cw0 * (int64_t)N, nvalid, beta, NWS, 0, scr, tm_base, L, bar_a, par, lane, false);
         } else if (S == M - 1) {
-          descent<M - 8, true, true, NS>(logit + cw0 * (int64_t)N, nvalid, beta, NWS, 0, scr, tm_base, L, bar_a, par, lane, scr_discard & ~1);
+          descent<M - 8, true, true, NS>(logit + cw0 * (int64_t)N, nvalid, beta, NWS, 0, scr, tm_base, L, bar_a, par, lane, false);
         } else {
           const int left_word = 4 * (i - (1 << (S - 7)));      // the left sibling's partial sums start at that block
           const float *sp = scr + (size_t)32 * ((1 << (S + 1)) - 512);
-          const int dis = scr_discard;
+          const bool dis = scr_discard != 0;
           switch (S) {                                         // source = scratch node of stage S+1, D = S+1-8
             case 8: if (!dead) descent<1, true, false, NS>(sp, 32, beta, NWS, left_word, scr, tm_base, L, bar_a, par, lane, dis); break;
             case 9: if (M > 10) descent<(M > 10 ? 2 : 1), true, false, NS>(sp, 32, beta, NWS, left_word, scr, tm_base, L, bar_a, par, lane, dis); break;
@@ -728,7 +718,7 @@ int launch_sc5_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t 
                                               // slots packed back to back: what this launch uses is one dense range (76 MB for
                                               // n = 1024, L2 resident); a sparse 4 MB stride made the L2 write every line back
                                               (size_t)warps * 32 * (N - 512) * 4,
-                                                      (env_int("POLAR_SC4_DISCARD", 1) & 1) | (env_int("POLAR_SC5_POL", 0) << 1), u_packed, u_info, info_pos, k);
+                                                      env_int("POLAR_SC4_DISCARD", 1), u_packed, u_info, info_pos, k);
   count_launch();
   POLAR_CHECK_LAUNCH("sc5_kernel");
   return POLAR_OK;
