@@ -274,9 +274,9 @@ def run_sweep(kind, world, dev, sampler, barrier, max_over_ranks):
             "api": "my_sn.sim.sim_ber_device(System_AWGN_model(...)) -- what sim_ber / PlotBER.simulate / main.py run",
             "scaling": "strong", "n_gpus": world, "batch_per_rank": bs, "wall_ms": ms, "wall_ms_runs": times,
             "simulated_codewords": blocks, "codewords_per_s": blocks / (ms * 1e-3), "info_gbit_per_s": blocks / (ms * 1e-3) * k / 1e9,
-            "iterations_counted": int(res[4].sum()), "iterations_queued": stats.get("queued"),
+            "iterations_counted": int(res[4].sum()), "iterations_queued": stats.get("queued"), "decoder_launches": stats.get("groups"),
             "bler": [float(v) for v in res[1]], "split_us_per_iteration": stats.get("split_us"),
-            "collective": "ncclAllReduce 4 x int64 per iteration" if world > 1 else "none (one rank)"}
+            "collective": "ncclAllReduce of the group's n_items x 4 int64 counters, one per decoder launch" if world > 1 else "none (one rank)"}
 
 
 def main():

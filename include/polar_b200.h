@@ -194,6 +194,22 @@ int polar_count_errors_f32(const float *d_b, const float *d_b_hat, int k, int64_
 int polar_mc_control(unsigned long long *d_delta4, long long *d_state8, long long target_bit_errs,
                      long long target_block_errs, long long max_mc_iter, void *stream);
 
+/* The same rules for a group of 1..POLAR_MC_GROUP_MAX queued iterations that may span SNR points (the Monte-Carlo loop packs
+ * several iterations into one decoder launch so that a small per-rank batch still fills the GPU; the outer loop of
+ * sim.py:79-133 and its early stop :128-133 move to the device with it).
+ *  d_delta        uint64[n_items,4]: counters of each iteration (all-reduced when sharded); cleared by the call.
+ *  h_item_point   HOST int32[n_items]: SNR-point index each iteration was simulated for (read during the call).
+ *  d_state        int64[n_points,8]: one polar_mc_control state row per SNR point (status 2 = no errors, early stop).
+ *  d_sweep8       int64[8]: [0] current point, [1] sweep ended, [2] iterations counted so far (= position in the random
+ *                 number sequence), [3] groups seen, [4] iterations of this group that counted.
+ *  expect_q       value of d_sweep8[2] the group was planned for; on a mismatch nothing counts.
+ * Iteration j counts only if all earlier ones of the group did, the sweep has not ended and the loop is at point
+ * h_item_point[j]; the first that does not ends the group. */
+#define POLAR_MC_GROUP_MAX 32
+int polar_mc_control_group(unsigned long long *d_delta, const int32_t *h_item_point, int n_items, long long *d_state,
+                           int n_points, long long *d_sweep8, long long expect_q, long long target_bit_errs,
+                           long long target_block_errs, long long max_mc_iter, int early_stop, void *stream);
+
 /* ---- N4: ordered-statistics decoder (my_sn/fec/osd/dec.py:8-192, OSDecoder.forward :149-191) -------------------
  * One CTA per codeword: reliability sort, most-reliable basis by the reference's pivot method (:99-117), hard decisions
  * on the pivots re-encoded, every error pattern of weight 1..t in itertools.combinations order (:57-62) under the

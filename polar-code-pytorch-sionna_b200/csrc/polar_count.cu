@@ -6,6 +6,8 @@
 
 namespace polar {
 
+constexpr int kMcGroupMax = POLAR_MC_GROUP_MAX;
+
 __device__ __forceinline__ unsigned warp_sum(unsigned v) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
@@ -71,9 +73,61 @@ __global__ void mc_control_kernel(unsigned long long *__restrict__ delta, long l
   delta[0] = 0; delta[1] = 0; delta[2] = 0; delta[3] = 0;
 }
 
+// The same rules for a GROUP of queued iterations that may span SNR points (my_sn/sim.py::sim_ber_device packs several
+// iterations -- of one point, or of consecutive points that are predicted to stop -- into one decoder launch so that a
+// small per-rank batch still fills the GPU).  Iteration j of the group was simulated at the noise level of point
+// item.point[j] with the random numbers of sequence position expect_q + j.  It counts only if it is what the sequential
+// loop (sim.py:79-133) would have run at that position: the sweep has not ended, every earlier iteration of the group
+// counted, and the loop is at that point.  The first iteration that does not count ends the group (its successors sit at
+// positions the loop will reach with other parameters); the host re-plans from the state it reads back.
+struct McItems { int point[kMcGroupMax]; };
+__global__ void mc_control_group_kernel(unsigned long long *__restrict__ delta, McItems item, int G, long long *__restrict__ state,
+                                        long long *__restrict__ sweep, long long expect_q, int P, long long target_bit,
+                                        long long target_block, long long max_iter, int early_stop) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  long long consumed = 0;
+  if (!sweep[1] && sweep[2] == expect_q) {
+    for (int j = 0; j < G; ++j) {
+      const long long pc = sweep[0];
+      if (pc >= P || item.point[j] != pc) break;
+      long long *st = state + 8 * pc;
+      st[0] += (long long)delta[4 * j]; st[1] += (long long)delta[4 * j + 1];
+      st[2] += (long long)delta[4 * j + 2]; st[3] += (long long)delta[4 * j + 3];
+      const long long it = ++st[6];
+      ++sweep[2]; ++consumed;
+      if (target_bit >= 0 && st[0] >= target_bit) { st[5] = 3; st[4] = 1; }             // sim.py:107-112
+      else if (target_block >= 0 && st[1] >= target_block) { st[5] = 4; st[4] = 1; }    // sim.py:113-118
+      else if (it >= max_iter) { st[5] = 1; st[4] = 1; }                                // sim.py:120-123
+      if (st[4]) {
+        if (early_stop && st[1] == 0) { st[5] = 2; sweep[1] = 1; break; }               // sim.py:128-133
+        sweep[0] = pc + 1;
+        if (pc + 1 >= P) { sweep[1] = 1; break; }
+      }
+    }
+  }
+  sweep[3] += 1; sweep[4] = consumed;
+  for (int j = 0; j < 4 * G; ++j) delta[j] = 0;
+}
+
 }  // namespace polar
 
 using namespace polar;
+
+extern "C" int polar_mc_control_group(unsigned long long *d_delta, const int32_t *h_item_point, int n_items,
+                                      long long *d_state, int n_points, long long *d_sweep8, long long expect_q,
+                                      long long target_bit_errs, long long target_block_errs, long long max_mc_iter,
+                                      int early_stop, void *stream) {
+  if (!d_delta || !h_item_point || !d_state || !d_sweep8) return set_error(POLAR_EINVAL, "mc_control_group: null pointer");
+  if (n_items < 1 || n_items > kMcGroupMax) return set_error(POLAR_EINVAL, "mc_control_group: 1 <= n_items <= %d", kMcGroupMax);
+  if (max_mc_iter < 1 || n_points < 1) return set_error(POLAR_EINVAL, "mc_control_group: max_mc_iter < 1 or n_points < 1");
+  McItems it;
+  for (int j = 0; j < kMcGroupMax; ++j) it.point[j] = j < n_items ? h_item_point[j] : -1;
+  mc_control_group_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_delta, it, n_items, d_state, d_sweep8, expect_q, n_points,
+                                                              target_bit_errs, target_block_errs, max_mc_iter, early_stop);
+  count_launch();
+  POLAR_CHECK_LAUNCH("mc_control_group");
+  return POLAR_OK;
+}
 
 extern "C" int polar_mc_control(unsigned long long *d_delta4, long long *d_state8, long long target_bit_errs,
                                 long long target_block_errs, long long max_mc_iter, void *stream) {

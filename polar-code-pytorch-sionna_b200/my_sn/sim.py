@@ -54,71 +54,104 @@ def _device_loop_ok(mc_fun, soft_estimates, count_fn):
           and tc.cuda.is_available())
 
 
-class StopPredictor:
-  """Should iteration ii+1 of an SNR point be queued before the stop flag of iteration ii has come back?
+class SweepPlanner:
+  """Which (SNR point, iteration) work items will the sequential loop of sim.py:79-133 run next?
 
-  The device loop never lets the GPU wait for the host inside a point: it queues one iteration ahead.  The price is one
-  discarded iteration per point (the one queued past the stop) -- 50 % of the work of a sweep whose points stop after a
-  single iteration (BASELINE configs[3]: 65536 block errors against a target of 1000).  So the look-ahead is skipped when
-  the counters seen so far say, with margin, that the iterations already queued will reach a target: rate per iteration
-  from this point's known iterations, else a tenth of the previous point's (error rates fall with Eb/N0).  Either
-  misprediction only costs time -- a discarded iteration or one host round trip -- never a different result."""
+  The device loop packs several items into one decoder launch (a per-rank batch of a few thousand codewords leaves the
+  last wave of a persistent kernel half empty) and keeps a second group queued behind the first.  An item that the
+  sequential loop would not have run at its position -- a point stopped earlier or later than planned -- is ignored by
+  the control kernel together with everything queued behind it, so a wrong plan only costs time, never a result.  The
+  planner therefore commits to a stop only when it is certain at ~3 sigma: from this point's counters so far, else from
+  bounds chained from the last finished point (error rates fall with Eb/N0: upper bound = the previous point's rate,
+  lower bound = `damp` times its lower bound).  Where the stop is uncertain the group ends at the earliest possible stop
+  and the next group waits for the counters.
 
-  def __init__(self, target_bit_errs, target_block_errs, max_mc_iter, damp=0.1, first_point_prior=None):
+  State of a plan: (point, iterations counted at it, lower / upper bound of its (bit, block) error counts so far)."""
+
+  def __init__(self, n_points, target_bit_errs, target_block_errs, max_mc_iter, per_iter_max, damp=0.3):
+    self.P = int(n_points)
     self.targets = (target_bit_errs, target_block_errs)
     self.max_iter = int(max_mc_iter)
-    self.damp = damp
-    # (bit errors, block errors) per iteration of the previous point; before the first point: the caller's prior (the
-    # device loop passes a block error rate of 1 and a bit error rate of 1/2 -- sweeps start at their lowest Eb/N0 --
-    # which `damp` turns into 0.1 / 0.05)
-    self.prev_rate = first_point_prior
-    self.start_point()
+    self.damp = float(damp)
+    # per-iteration (bit, block) error rate bounds of the last finished point; before the first: the most a batch can hold
+    self.prev_hi = tuple(float(v) for v in per_iter_max)
+    self.prev_lo = tuple(float(v) * self.damp for v in per_iter_max)
 
-  def start_point(self):
-    self.known_iters, self.known = 0, (0, 0)
+  def finished_point(self, iters, bit_errs, block_errs):
+    """Counters of the point that just finished: the next points' rates are bounded by them."""
+    if iters > 0:
+      r = (bit_errs / iters, block_errs / iters)
+      self.prev_hi = tuple(v + 3.0 * (v / iters) ** 0.5 + 1.0 / iters for v in r)
+      self.prev_lo = tuple(max(v - 3.0 * (v / iters) ** 0.5 - 1.0 / iters, 0.0) * self.damp for v in r)
 
-  def observe(self, iters, bit_errs, block_errs):
-    self.known_iters, self.known = int(iters), (int(bit_errs), int(block_errs))
-
-  def end_point(self):
-    if self.known_iters:
-      self.prev_rate = tuple(c / self.known_iters for c in self.known)
-
-  def speculate(self, queued):
-    """queued: iterations of this point already queued (results of the last queued - known_iters unknown)."""
-    if queued >= self.max_iter:
-      return False
-    if self.known_iters:
-      rate = tuple(c / self.known_iters for c in self.known)
-    elif self.prev_rate is not None:
-      rate = tuple(c * self.damp for c in self.prev_rate)
-    else:
-      return True
-    for tgt, cum, r in zip(self.targets, self.known, rate):
+  def _stop_range(self, cum_lo, cum_hi, lo, hi, rem):
+    """(earliest possible, surely reached) number of further iterations until a target stops the point, both <= rem."""
+    r_lo = r_hi = rem
+    for t in range(2):
+      tgt = self.targets[t]
       if tgt is None:
         continue
-      pred = cum + r * (queued - self.known_iters)
-      if pred >= tgt + 3.0 * pred ** 0.5 + 1.0:
-        return False                 # the queued iterations will (almost surely) reach the target: wait for the flag
-    return True
+      for r in range(1, rem + 1):
+        if cum_hi[t] + r * hi[t] + 3.0 * (r * hi[t]) ** 0.5 + 1.0 >= tgt:
+          r_lo = min(r_lo, r)
+          break
+      for r in range(1, rem + 1):
+        if cum_lo[t] + r * lo[t] - 3.0 * (r * lo[t]) ** 0.5 - 1.0 >= tgt:
+          r_hi = min(r_hi, r)
+          break
+    return r_lo, max(r_hi, r_lo)
+
+  def plan(self, state, gmax):
+    """state = (point, iters, cum_lo, cum_hi) -> (items: list of point indices, state after them or None when the last
+    item may or may not stop its point, "done" when the plan reaches the end of the sweep)."""
+    p, it, cum_lo, cum_hi = state
+    items = []
+    chain_lo, chain_hi = self.prev_lo, self.prev_hi
+    while len(items) < gmax and p < self.P:
+      if it > 0:      # this point's own counters bound its rate
+        lo = tuple(max(c / it - 3.0 * (c / it / it) ** 0.5 - 1.0 / it, 0.0) for c in cum_lo)
+        hi = tuple(c / it + 3.0 * (c / it / it) ** 0.5 + 1.0 / it for c in cum_hi)
+      else:
+        lo, hi = chain_lo, chain_hi
+      rem = self.max_iter - it
+      r_lo, r_hi = self._stop_range(cum_lo, cum_hi, lo, hi, rem)
+      take = min(r_lo, gmax - len(items))
+      items += [p] * take
+      it += take
+      cum_lo = tuple(c + max(take * l - 3.0 * (take * l) ** 0.5, 0.0) for c, l in zip(cum_lo, lo))
+      cum_hi = tuple(c + take * h + 3.0 * (take * h) ** 0.5 + 1.0 for c, h in zip(cum_hi, hi))
+      if take < r_lo:
+        return items, (p, it, cum_lo, cum_hi)          # group full, the point surely goes on
+      if r_lo != r_hi:
+        return items, None                             # it may stop here or later: wait for the counters
+      chain_lo, chain_hi = tuple(v * self.damp for v in lo), hi
+      p, it, cum_lo, cum_hi = p + 1, 0, (0.0, 0.0), (0.0, 0.0)
+    return items, ("done" if p >= self.P else (p, it, cum_lo, cum_hi))
 
 
 def sim_ber_device(model, ebno_dbs, batch_size, max_mc_iter, target_bit_errs=None, target_block_errs=None,
-                   early_stop=True, verbose=True, return_counters=False, lookahead=True, stats=None, profile=False):
-  """the Monte-Carlo loop of sim.py:79-133 with every per-iteration step on the device.
+                   early_stop=True, verbose=True, return_counters=False, lookahead=True, stats=None, profile=False,
+                   group_mb=4096):
+  """the Monte-Carlo loop of sim.py:79-133 with every step on the device, the stop rules included.
 
-  One iteration = front-end kernel (bits -> encoder -> QPSK -> AWGN -> logits; `model.device_frontend`) -> decoder kernel
-  (bit-packed decisions) -> packed error counter -> [sharded: one 4 x int64 NCCL all-reduce] -> `polar_mc_control`, a
-  one-thread kernel that accumulates the counters and evaluates the stop rules (target bit errors, target block errors,
-  max iterations).  All buffers are allocated once per call.  The host never reads a counter synchronously inside an SNR
-  point: it keeps ONE iteration queued ahead (unless `StopPredictor` says the queued work will reach a target) and polls
-  the stop flag of the iteration before from pinned memory; an iteration queued past the stop is ignored by the control
-  kernel and its random numbers are handed to the next point, which makes the result identical to the host loop
-  (`sim_ber(..., on_device=False)`) for the same seed.
+  Work item = one iteration of one SNR point: front-end kernel (bits -> encoder -> QPSK -> AWGN -> logits;
+  `model.device_frontend`) into a slice of the group's buffers.  A GROUP of up to 32 items (`SweepPlanner`: further
+  iterations of the point, then the first iterations of the following points where the current one is certain to stop)
+  shares ONE decoder launch (bit-packed decisions), then per item a packed error count, [sharded: ONE NCCL all-reduce
+  of the group's n_items x 4 int64 counters] and `polar_mc_control_group`, a one-thread kernel that walks the items in
+  order through the stop rules (target bit errors, target block errors, max iterations, early stop at an error-free
+  point) and ignores every item the sequential loop would not have run at that position.  Item number q of the sweep
+  always draws the random numbers of offset q x batch, so ignored items hand theirs to whatever runs there next and
+  the result is identical to the host loop (`sim_ber(..., on_device=False)`) for the same seed, however the items
+  were grouped.  Why groups: split over 8 ranks a batch of 2^16 codewords leaves 8192 per rank = 3.46 waves of the
+  list decoder's persistent grid (6.98x at 8 GPUs from the decoder alone); four such items per launch fill it.
+  All buffers are allocated once per call (`group_mb` MiB of logits per group, two groups); the host reads a group's
+  outcome (the sweep cursor and the per-point counters) from pinned memory while the next group is already queued.
+  `lookahead=False`: one item per group, nothing queued ahead (queued == counted).
   Returns (ber, bler) like sim_ber; with return_counters also the int64 [P,4] counters, status and iterations.
-  `stats` (dict, optional) receives {"queued": iterations launched, "counted": iterations counted}; with `profile`
-  also "split_us": mean device time per iteration of front end / decoder / counter / all-reduce / control (CUDA events
-  on the launching stream at the stage boundaries) and the host wall time per iteration."""
+  `stats` (dict, optional) receives {"queued": items launched, "counted": items counted, "groups": decoder launches};
+  with `profile` also "split_us": mean device time per ITEM of front end / decoder / counter / all-reduce / control
+  (CUDA events on the launching stream at the stage boundaries of each group) and the host wall time per item."""
   dist = _dist()
   rank0 = dist is None or dist.get_rank() == 0
   verbose = verbose and rank0
@@ -138,26 +171,34 @@ def sim_ber_device(model, ebno_dbs, batch_size, max_mc_iter, target_bit_errs=Non
   status = np.zeros(P, dtype=np.int64)
   iters = np.zeros(P, dtype=np.int64)
   runtime = np.zeros(P)
-  n_queued = 0
   status_levels = ["not simulated", "reached max iter       ", "no errors - early stop",
                    "reached target bit errors", "reached target block errors"]
   fmt = "{: >9} |{: >11} |{: >11} |{: >12} |{: >12} |{: >13} |{: >12} |{: >12} |{: >10}"
-  DEPTH = 2 if lookahead else 1
   world = dist.get_world_size() if dist is not None else 1
-  pred = StopPredictor(target_bit_errs, target_block_errs, max_mc_iter,
-                       first_point_prior=(0.5 * B * tables.k * world, 1.0 * B * world))
+  DEPTH = 2 if lookahead else 1
+  gmax = 1
+  if lookahead:
+    gmax = int(max(1, min(dk.MC_GROUP_MAX, (int(group_mb) << 20) // max(B * model.n * 4, 1), P * max_mc_iter)))
+  planner = SweepPlanner(P, target_bit_errs, target_block_errs, max_mc_iter,
+                         per_iter_max=(0.5 * B * tables.k * world, 1.0 * B * world))
+  if P == 0:
+    z = tc.zeros(0, dtype=tc.float32)
+    return (z, z, counters, status, iters) if return_counters else (z, z)
+  offset_start = model._offset
+  n_items = n_groups = 0
+  marks = []                                                 # profile: (n_items, 6 timing events) per group
   with tc.cuda.device(dev):
     nw = dk.words(model.n)
-    u_tx = tc.empty((B, nw), dtype=tc.int32, device=dev)
-    llr = tc.empty((B, model.n), dtype=tc.float32, device=dev)
-    u_hat = tc.empty((B, nw), dtype=tc.int32, device=dev)
-    state = tc.zeros(8, dtype=tc.int64, device=dev)
-    delta = tc.zeros(4, dtype=tc.int64, device=dev)
+    state = tc.zeros((P, 8), dtype=tc.int64, device=dev)
+    sweep = tc.zeros(8, dtype=tc.int64, device=dev)
     sizes = tc.tensor([0, 0, B * tables.k, B], dtype=tc.int64, device=dev)
-    host = [tc.zeros(8, dtype=tc.int64).pin_memory() for _ in range(DEPTH)]
-    events = [tc.cuda.Event() for _ in range(DEPTH)]
-
-    marks = []                                               # profile: 6 timing events per queued iteration
+    slots = []
+    for _ in range(DEPTH):
+      slots.append(dict(u_tx=tc.empty((gmax * B, nw), dtype=tc.int32, device=dev),
+                        llr=tc.empty((gmax * B, model.n), dtype=tc.float32, device=dev),
+                        u_hat=tc.empty((gmax * B, nw), dtype=tc.int32, device=dev),
+                        delta=tc.zeros((gmax, 4), dtype=tc.int64, device=dev),
+                        host=tc.zeros((P + 1, 8), dtype=tc.int64).pin_memory(), event=tc.cuda.Event()))
 
     def mark(row):
       if profile:
@@ -165,75 +206,97 @@ def sim_ber_device(model, ebno_dbs, batch_size, max_mc_iter, target_bit_errs=Non
         e.record()
         row.append(e)
 
-    def queue(i, ii, offset0):
+    def queue(slot, items, q0):
+      G = len(items)
       row = []
       mark(row)
-      model.device_frontend(tables, B, ebno_dbs[i], model._seed, offset0 + ii * B, (u_tx, llr))
+      for j, p in enumerate(items):
+        model.device_frontend(tables, B, ebno_dbs[p], model._seed, offset_start + (q0 + j) * B,
+                              (slot["u_tx"][j * B:(j + 1) * B], slot["llr"][j * B:(j + 1) * B]))
       mark(row)
-      dec.decode_packed(llr, tables, out=u_hat)
+      dec.decode_packed(slot["llr"][:G * B], tables, out=slot["u_hat"][:G * B])
       mark(row)
-      delta.copy_(sizes)                                     # (0, 0, bits, blocks) of this rank's shard
-      dk.count_errors_packed(u_tx, u_hat, tables.info_mask, model.n, delta)
+      delta = slot["delta"][:G]
+      delta.copy_(sizes.expand(G, 4))                        # (0, 0, bits, blocks) of this rank's shard, per item
+      for j in range(G):
+        dk.count_errors_packed(slot["u_tx"][j * B:(j + 1) * B], slot["u_hat"][j * B:(j + 1) * B], tables.info_mask,
+                               model.n, delta[j])
       mark(row)
       if dist is not None:
-        dist.all_reduce(delta)                               # stream-ordered NCCL all-reduce of 4 x int64
+        dist.all_reduce(delta)                               # stream-ordered NCCL all-reduce of G x 4 int64
       mark(row)
-      dk.mc_control(delta, state, target_bit_errs, target_block_errs, max_mc_iter)
-      host[ii % DEPTH].copy_(state, non_blocking=True)
-      events[ii % DEPTH].record()
+      dk.mc_control_group(delta, items, state, sweep, q0, target_bit_errs, target_block_errs, max_mc_iter, early_stop)
+      slot["host"][:P].copy_(state, non_blocking=True)
+      slot["host"][P].copy_(sweep, non_blocking=True)
+      slot["event"].record()
       mark(row)
       if profile:
-        marks.append(row)
+        marks.append((G, row))
 
-    for i in range(P):
-      t0 = time.perf_counter()
-      state.zero_()
-      offset0 = model._offset
-      pred.start_point()
-      queued = known = 0
-      while True:
-        if queued < max_mc_iter and queued - known < DEPTH and (queued == known or pred.speculate(queued)):
-          queue(i, queued, offset0)
-          queued += 1
-          continue
-        if known == queued:
-          break
-        events[known % DEPTH].synchronize()                  # oldest iteration whose outcome is still unknown
-        h = host[known % DEPTH]
-        known += 1
-        pred.observe(int(h[6]), int(h[0]), int(h[1]))
-        if int(h[4]):
-          break
-      n_queued += queued
-      tc.cuda.current_stream(dev).synchronize()
-      st = state.cpu().numpy()
-      pred.observe(int(st[6]), int(st[0]), int(st[1]))
-      pred.end_point()
-      counters[i] = st[:4]; status[i] = st[5]; iters[i] = st[6]
-      model._offset = offset0 + int(st[6]) * B                 # random numbers of a discarded iteration are reused
-      runtime[i] = time.perf_counter() - t0
-      if verbose:
-        if i == 0:
-          print(fmt.format("EbNo [dB]", "BER", "BLER", "bit errors", "num bits", "block errors", "num blocks",
-                           "runtime [s]", "status")); print('-' * 135)
-        ber_i = counters[i, 0] / counters[i, 2] if counters[i, 2] else 0.0
-        bler_i = counters[i, 1] / counters[i, 3] if counters[i, 3] else 0.0
-        print(fmt.format(str(np.round(ebno_dbs[i], 3)), f"{ber_i:.4e}", f"{bler_i:.4e}", int(counters[i, 0]),
-                         int(counters[i, 2]), int(counters[i, 1]), int(counters[i, 3]), np.round(runtime[i], 1),
-                         status_levels[int(status[i])]))
-      if early_stop and counters[i, 1] == 0:                   # sim.py:128-133
-        status[i] = 2
-        if verbose:
-          print(f"\nSimu stopped as no error occurred @ EbNo = {ebno_dbs[i]:.1f} dB.\n")
+    known = (0, 0, (0.0, 0.0), (0.0, 0.0))                   # what the counters read back so far say
+    q_known = 0
+    pred, q_pred = known, 0                                  # state the queued groups lead to, if the plan holds
+    inflight = []
+    reported = 0                                             # points whose result line has been printed / timed
+    t_point = time.perf_counter()
+    nslot = 0
+    finished = False
+    while not finished:
+      if pred is not None and pred != "done" and len(inflight) < DEPTH:
+        items, after = planner.plan(pred, gmax)
+        slot = slots[nslot % DEPTH]; nslot += 1
+        queue(slot, items, q_pred)
+        n_items += len(items); n_groups += 1
+        inflight.append((slot, items, after, q_pred))
+        pred, q_pred = after, q_pred + len(items)
+        continue
+      if not inflight:
         break
+      slot, items, after, q0 = inflight.pop(0)
+      slot["event"].synchronize()
+      h = slot["host"].numpy()
+      pc, ended, q_known = int(h[P, 0]), bool(h[P, 1]), int(h[P, 2])
+      while reported < min(pc + (1 if ended and pc < P else 0), P):      # points that finished since the last look
+        st = h[reported]
+        counters[reported] = st[:4]; status[reported] = st[5]; iters[reported] = st[6]
+        planner.finished_point(int(st[6]), int(st[0]), int(st[1]))
+        now = time.perf_counter()
+        runtime[reported] = now - t_point; t_point = now
+        if verbose:
+          i = reported
+          if i == 0:
+            print(fmt.format("EbNo [dB]", "BER", "BLER", "bit errors", "num bits", "block errors", "num blocks",
+                             "runtime [s]", "status")); print('-' * 135)
+          ber_i = counters[i, 0] / counters[i, 2] if counters[i, 2] else 0.0
+          bler_i = counters[i, 1] / counters[i, 3] if counters[i, 3] else 0.0
+          print(fmt.format(str(np.round(ebno_dbs[i], 3)), f"{ber_i:.4e}", f"{bler_i:.4e}", int(counters[i, 0]),
+                           int(counters[i, 2]), int(counters[i, 1]), int(counters[i, 3]), np.round(runtime[i], 1),
+                           status_levels[int(status[i])]))
+          if status[i] == 2:
+            print(f"\nSimu stopped as no error occurred @ EbNo = {ebno_dbs[i]:.1f} dB.\n")
+        reported += 1
+      if ended or pc >= P:
+        finished = True
+        break
+      cum = (float(h[pc, 0]), float(h[pc, 1]))
+      known = (pc, int(h[pc, 6]), cum, cum)
+      as_planned = q_known == q0 + len(items) and (after is None or (after != "done" and after[0] == pc and after[1] == known[1]))
+      if not as_planned:
+        inflight.clear()                                     # whatever is queued behind was planned on a wrong premise:
+        pred, q_pred = known, q_known                        # the control kernel ignores it; plan again from the counters
+      elif not inflight:
+        pred, q_pred = known, q_known                        # nothing queued ahead: plan from the exact counters
+    tc.cuda.current_stream(dev).synchronize()
+    model._offset = offset_start + q_known * B               # random numbers of ignored items are used again
   if stats is not None:
-    stats.update(queued=int(n_queued), counted=int(iters.sum()), blocks=int(counters[:, 3].sum()))
+    stats.update(queued=int(n_items), counted=int(iters.sum()), blocks=int(counters[:, 3].sum()), groups=int(n_groups))
     if profile and marks:
       tc.cuda.synchronize(dev)
       names = ("front_end", "decode", "count", "all_reduce", "control")
-      split = {nm: float(np.mean([r[j].elapsed_time(r[j + 1]) for r in marks])) * 1e3 for j, nm in enumerate(names)}
-      split["device_total"] = float(np.mean([r[0].elapsed_time(r[5]) for r in marks])) * 1e3
-      split["host_wall"] = float(runtime.sum()) / max(len(marks), 1) * 1e6
+      tot = float(sum(g for g, _ in marks))
+      split = {nm: float(sum(r[j].elapsed_time(r[j + 1]) for _, r in marks)) / tot * 1e3 for j, nm in enumerate(names)}
+      split["device_total"] = float(sum(r[0].elapsed_time(r[5]) for _, r in marks)) / tot * 1e3
+      split["host_wall"] = float(runtime.sum()) / tot * 1e6
       stats["split_us"] = split
   with np.errstate(divide='ignore', invalid='ignore'):
     ber = np.nan_to_num(counters[:, 0] / counters[:, 2])

@@ -68,6 +68,8 @@ _SIGNATURES = {
   "polar_count_errors_packed": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
   "polar_count_errors_f32": (_i32, [_vp, _vp, _i32, _i64, _vp, _vp]),
   "polar_mc_control": (_i32, [_vp, _vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, _vp]),
+  "polar_mc_control_group": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong,
+                                    ctypes.c_longlong, _i32, _vp]),
   "polar_osd_decode": (_i32, [_vp, _vp, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp]),
   "polar_scl3_math_selftest": (_i32, [ctypes.c_uint64, _vp, _vp]),
   "polar_pack_bits_f32": (_i32, [_vp, _i32, _i64, _vp, _vp]),
@@ -441,6 +443,21 @@ def mc_control(delta, state, target_bit_errs, target_block_errs, max_mc_iter):
   tk = -1 if target_block_errs is None else int(target_block_errs)
   with tc.cuda.device(dev):
     check(lib().polar_mc_control(ptr(delta), ptr(state), tb, tk, int(max_mc_iter), stream_ptr(dev)))
+
+
+MC_GROUP_MAX = 32
+
+
+def mc_control_group(delta, item_points, state, sweep, expect_q, target_bit_errs, target_block_errs, max_mc_iter, early_stop):
+  """polar_mc_control_group: fold the counters delta [G,4] of a group of queued iterations (SNR point of iteration j =
+  item_points[j]) into the per-point states [P,8] and the sweep cursor [8], with sim_ber's stop rules, on the device."""
+  dev = state.device
+  tb = -1 if target_bit_errs is None else int(target_bit_errs)
+  tk = -1 if target_block_errs is None else int(target_block_errs)
+  pts = (ctypes.c_int32 * len(item_points))(*[int(p) for p in item_points])
+  with tc.cuda.device(dev):
+    check(lib().polar_mc_control_group(ptr(delta), ctypes.cast(pts, ctypes.c_void_p), len(item_points), ptr(state), state.shape[0],
+                                       ptr(sweep), int(expect_q), tb, tk, int(max_mc_iter), 1 if early_stop else 0, stream_ptr(dev)))
 
 
 def pack_rows(m):

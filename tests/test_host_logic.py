@@ -246,35 +246,41 @@ def test_main_cli_fallback_parser_follows_the_annotations():
     assert (d.k, d.n, d.bs, d.snr_end, d.seed) == (32, 64, 3, 5, 42)
 
 
-def test_stop_predictor_of_the_device_monte_carlo_loop():
-    """my_sn/sim.py::StopPredictor: look-ahead is skipped only when the counters seen so far say, with margin, that the
-    queued iterations reach a target; it can never change a result (the control kernel ignores surplus iterations)."""
-    from my_sn.sim import StopPredictor
-    p = StopPredictor(None, 1000, 16)
-    assert p.speculate(1)                                  # nothing known, no previous point: queue ahead
-    p.observe(1, 10 ** 7, 65536); p.end_point()            # configs[3]: every block in error at the first point
-    p.start_point()
-    assert not p.speculate(1)                              # a tenth of 65536 still clears 1000 with margin: wait for the flag
-    p.observe(1, 10 ** 6, 17000); p.end_point()
-    p.start_point()
-    assert not p.speculate(1)
-    p.observe(1, 2000, 150); p.end_point()                 # waterfall region: 150 errors per iteration
-    p.start_point()
-    assert p.speculate(1)                                  # 15 predicted: far from the target
-    p.observe(1, 900, 60)
-    assert p.speculate(2)
-    p.observe(15, 13000, 900)
-    assert p.speculate(15) and not p.speculate(16)         # max_mc_iter caps the queue
-    p.observe(6, 50000, 900)
-    assert p.speculate(7)                                  # 900 + 150 = 1050 < 1000 + 3 sigma: not confident, keep the GPU busy
-    p.observe(6, 50000, 990)
-    assert not p.speculate(7)                              # 990 + 165 = 1155 clears the target with margin
-    q = StopPredictor(5000, None, 4)
-    q.observe(1, 4000, 1)
-    assert not q.speculate(2)                              # 8000 predicted bit errors against 5000
-    q = StopPredictor(None, None, 3)
-    q.observe(1, 1, 1)
-    assert q.speculate(1) and q.speculate(2) and not q.speculate(3)
+def test_sweep_planner_of_the_device_monte_carlo_loop():
+    """my_sn/sim.py::SweepPlanner: which (point, iteration) items the device loop packs into one decoder launch.  A plan
+    crosses into the next SNR point only where the current one is certain (3 sigma) to stop; a wrong plan can never change
+    a result (the control kernel ignores items the sequential loop would not have run), it only wastes the ignored items."""
+    from my_sn.sim import SweepPlanner
+    start = (0, 0, (0.0, 0.0), (0.0, 0.0))
+    # configs[3]: 65536 codewords per iteration, target 1000 block errors, every point far above it
+    p = SweepPlanner(9, None, 1000, 16, per_iter_max=(0.5 * 65536 * 1024, 65536.0))
+    items, after = p.plan(start, 32)
+    assert items == [0, 1, 2, 3] and after is None          # chained lower bound 65536 x 0.3^j: certain for 3 points, the 4th is open
+    p.finished_point(1, 3 * 10 ** 7, 65530)
+    items, after = p.plan((4, 0, (0.0, 0.0), (0.0, 0.0)), 32)
+    assert items == [4, 5, 6, 7] and after is None
+    p.finished_point(1, 10 ** 7, 45000)
+    items, after = p.plan((8, 0, (0.0, 0.0), (0.0, 0.0)), 32)
+    assert items == [8] and after == "done"
+    # waterfall region: 150 block errors per iteration known at this point -> 6 or 7 more iterations, uncertain which
+    p = SweepPlanner(9, None, 1000, 16, per_iter_max=(1e9, 65536.0))
+    items, after = p.plan((3, 1, (900.0, 150.0), (900.0, 150.0)), 32)
+    assert set(items) == {3} and 4 <= len(items) <= 6 and after is None     # up to the earliest possible stop, then wait
+    # no targets: the whole sweep is certain -- groups are cut by size only and chain across points
+    p = SweepPlanner(3, None, None, 16, per_iter_max=(1.0, 1.0))
+    items, after = p.plan(start, 8)
+    assert items == [0] * 8 and after[:2] == (0, 8)
+    items, after = p.plan(after, 12)
+    assert items == [0] * 8 + [1] * 4 and after[:2] == (1, 4)
+    items, after = p.plan((2, 10, (0.0, 0.0), (0.0, 0.0)), 32)
+    assert items == [2] * 6 and after == "done"
+    # a bit-error target decides as well; max_mc_iter caps every point
+    p = SweepPlanner(2, 5000, None, 4, per_iter_max=(1e6, 1e3))
+    items, after = p.plan((0, 1, (4000.0, 1.0), (4000.0, 1.0)), 32)
+    assert items[:1] == [0] and items.count(0) == 1          # 8000 predicted bit errors against 5000: stops after one more
+    p = SweepPlanner(2, None, 10 ** 6, 12, per_iter_max=(512 * 64 * 0.5, 512.0))
+    items, after = p.plan(start, 32)
+    assert items == [0] * 12 + [1] * 12 and after == "done"  # target out of reach: max_mc_iter iterations per point
 
 
 def test_encoder_rejects_non_arikan_generator():
