@@ -228,7 +228,7 @@ PDEV uint32_t leaf4(const float (&x)[4], uint32_t fm, uint32_t &u) {
   const bool u1 = n1 & (l1 <= 0.0f);
   const bool p0 = u0 != u1;                      // partial sums of the left pair: (u0^u1, u1)
   const float b0 = p0 ? d0 : s0, b1 = u1 ? d1 : s1;
-  const float l2 = f_minsum(b0, b1);
+  const float l2 = f_minsum_noclip(b0, b1);      // a leaf LLR is only compared with 0: the +-30 clip cannot change that
   const float sb = b0 + b1, db = b1 - b0;
   const bool u2 = n2 & (l2 <= 0.0f);
   const float l3 = u2 ? db : sb;
@@ -268,9 +268,13 @@ struct RollTree<3> {
 // ---- partial-sum-only subtrees (polar_sc3.cu) -------------------------------------------------------
 // The decisions of a node are the polar transform of its partial sums (u = T(beta), T an involution), so
 // the serial per-lane path only has to produce beta; u is recovered once per codeword at the end.
+// CL: the node's LLRs are outputs of an f (a left child), i.e. already inside [-30, 30] -- the clip of the first f level is
+// then the identity and costs nothing (one FMNMX.XORSIGN instead of two, on the serial path).
+template <bool CL = false>
 PDEV uint32_t leaf4_beta(const float (&x)[4], uint32_t fm) {
   const bool n0 = !(fm & 1u), n1 = !(fm & 2u), n2 = !(fm & 4u), n3 = !(fm & 8u);
-  const float a0 = f_minsum(x[0], x[2]), a1 = f_minsum(x[1], x[3]);
+  const float a0 = CL ? f_minsum_noclip(x[0], x[2]) : f_minsum(x[0], x[2]);
+  const float a1 = CL ? f_minsum_noclip(x[1], x[3]) : f_minsum(x[1], x[3]);
   const float s0 = x[0] + x[2], d0 = x[2] - x[0], s1 = x[1] + x[3], d1 = x[3] - x[1];
   const float l0 = f_minsum_noclip(a0, a1);
   const float sa = a0 + a1, da = a1 - a0;
@@ -279,7 +283,7 @@ PDEV uint32_t leaf4_beta(const float (&x)[4], uint32_t fm) {
   const bool u1 = n1 & (l1 <= 0.0f);
   const bool p0 = u0 != u1;                      // partial sums of the left pair: (u0^u1, u1)
   const float b0 = p0 ? d0 : s0, b1 = u1 ? d1 : s1;
-  const float l2 = f_minsum(b0, b1);
+  const float l2 = f_minsum_noclip(b0, b1);      // a leaf LLR is only compared with 0: the +-30 clip cannot change that
   const float sb = b0 + b1, db = b1 - b0;
   const bool u2 = n2 & (l2 <= 0.0f);
   const float l3 = u2 ? db : sb;
@@ -292,7 +296,81 @@ PDEV bool rate1_beta(const float (&x)[1 << T], uint32_t &beta) {
   uint32_t u;
   return rate1_decide<T>(x, beta, u);      // the transform of u is dead code here and is removed
 }
-template <int T>
+// CL: the node's LLRs are outputs of an f (the node is a left child), already inside [-30, 30]: the first f level below it
+// needs no clip.  Known at compile time wherever the two children of a node are separate calls (16 leaves and below);
+// the rolled levels above pass CL = false.  (A warp-uniform run-time flag for those levels was measured: the extra uniform
+// branches on the serial path cost more than the 8 .. 64 FMNMX they save, 2.16 -> 2.27 ms at n = 1024.)
+template <int T, bool CL = false>
+struct BetaTree;
+template <bool CL>
+struct BetaTree<3, CL> {
+  PDEV static uint32_t run(const float (&x)[8], uint32_t fm) {
+    fm &= 0xFFu;
+    if (fm == 0xFFu) return 0;
+    float y[4], sd[4], df[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      y[j] = CL ? f_minsum_noclip(x[j], x[j + 4]) : f_minsum(x[j], x[j + 4]);
+      sd[j] = x[j] + x[j + 4]; df[j] = x[j + 4] - x[j];
+    }
+    const uint32_t bl = leaf4_beta<true>(y, fm & 0xFu);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = ((bl >> j) & 1u) ? df[j] : sd[j];
+    const uint32_t br = leaf4_beta<false>(y, fm >> 4);
+    return (bl ^ br) | (br << 4);
+  }
+};
+// 16 leaves: the two children are separate calls, so each knows whether its LLRs come from an f (left) or a g (right)
+template <bool CL>
+struct BetaTree<4, CL> {
+  PDEV static uint32_t run(const float (&x)[16], uint32_t fm) {
+    fm &= 0xFFFFu;
+    if (fm == 0xFFFFu) return 0;
+    if (fm == 0) {
+      uint32_t b;
+      if (rate1_beta<4>(x, b)) return b;
+    }
+    float y[8];
+    uint32_t bl = 0, br = 0;
+    if ((fm & 0xFFu) != 0xFFu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = CL ? f_minsum_noclip(x[j], x[j + 8]) : f_minsum(x[j], x[j + 8]);
+      bl = BetaTree<3, true>::run(y, fm & 0xFFu);
+    }
+    if ((fm >> 8) != 0xFFu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = g_minsum(x[j], x[j + 8], (bl << (31 - j)) & 0x80000000u);
+      br = BetaTree<3, false>::run(y, fm >> 8);
+    }
+    return (bl ^ br) | (br << 8);
+  }
+};
+#if defined(POLAR_BT5_UNROLL)
+template <bool CL>
+struct BetaTree<5, CL> {
+  PDEV static uint32_t run(const float (&x)[32], uint32_t fm) {
+    if (fm == 0xFFFFFFFFu) return 0;
+    if (fm == 0) {
+      uint32_t b;
+      if (rate1_beta<5>(x, b)) return b;
+    }
+    float y[16];
+    uint32_t bl = 0, br = 0;
+    if ((fm & 0xFFFFu) != 0xFFFFu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) y[j] = CL ? f_minsum_noclip(x[j], x[j + 16]) : f_minsum(x[j], x[j + 16]);
+      bl = BetaTree<4, true>::run(y, fm & 0xFFFFu);
+    }
+    if ((fm >> 16) != 0xFFFFu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) y[j] = g_minsum(x[j], x[j + 16], (bl << (31 - j)) & 0x80000000u);
+      br = BetaTree<4, false>::run(y, fm >> 16);
+    }
+    return (bl ^ br) | (br << 16);
+  }
+};
+#endif
+template <int T, bool CL>
 struct BetaTree {   // rolled two-iteration loop per level, like RollTree
   static constexpr int N = 1 << T, H = N / 2;
   static constexpr uint32_t FULL = (N == 32) ? 0xFFFFFFFFu : ((1u << N) - 1u);
@@ -312,7 +390,7 @@ struct BetaTree {   // rolled two-iteration loop per level, like RollTree
       if (fmc == HALF) { bc = 0; continue; }
       if (h == 0) {
 #pragma unroll
-        for (int j = 0; j < H; ++j) y[j] = f_minsum(x[j], x[j + H]);
+        for (int j = 0; j < H; ++j) y[j] = CL ? f_minsum_noclip(x[j], x[j + H]) : f_minsum(x[j], x[j + H]);
       } else {
 #pragma unroll
         for (int j = 0; j < H; ++j) y[j] = g_minsum(x[j], x[j + H], (bl << (31 - j)) & 0x80000000u);
@@ -321,21 +399,6 @@ struct BetaTree {   // rolled two-iteration loop per level, like RollTree
       if (h == 0) bl = bc;
     }
     return (bl ^ bc) | (bc << H);
-  }
-};
-template <>
-struct BetaTree<3> {
-  PDEV static uint32_t run(const float (&x)[8], uint32_t fm) {
-    fm &= 0xFFu;
-    if (fm == 0xFFu) return 0;
-    float y[4], sd[4], df[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { y[j] = f_minsum(x[j], x[j + 4]); sd[j] = x[j] + x[j + 4]; df[j] = x[j + 4] - x[j]; }
-    const uint32_t bl = leaf4_beta(y, fm & 0xFu);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) y[j] = ((bl >> j) & 1u) ? df[j] : sd[j];
-    const uint32_t br = leaf4_beta(y, fm >> 4);
-    return (bl ^ br) | (br << 4);
   }
 };
 

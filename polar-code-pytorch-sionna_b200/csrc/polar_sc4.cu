@@ -16,6 +16,9 @@
 //     storage); stages 7 and 6 plus the partial-sum words in shared memory (916 B per codeword).
 //   * only partial sums are produced on the serial path; the decisions are recovered once per codeword as
 //     u = T(x_hat).
+// the 32-leaf level as two separate calls (its children then know at compile time whether their LLRs come from an f and
+// skip the clip): +1.5 % here; the larger polar_sc5.cu kernel loses 5 % to the extra code (instruction cache) and keeps it rolled
+#define POLAR_BT5_UNROLL 1
 #include "polar_common.cuh"
 #include "polar_internal.h"
 

@@ -35,8 +35,37 @@ template <int T> int check(int iters) {
   }
   return bad;
 }
+// BetaTree<5> (the partial-sum-only recursion the kernels run): equal to SubTree's partial sums; with cl = true on inputs
+// inside [-30, 30] (outputs of an f) the clip-free first level must not change anything
+static int check_beta(int iters) {
+  int bad = 0;
+  for (int it = 0; it < iters; ++it) {
+    float x[32]; uint32_t fm = 0;
+    const int mode = it % 5;
+    for (int j = 0; j < 32; ++j) {
+      float v = ((int)(rnd() % 8001) - 4000) / 100.0f;           // [-40, 40]: g outputs of the levels below exceed the clip
+      if (mode == 1) v = roundf(v);
+      if (mode == 2 && rnd() % 4 == 0) v = 0.0f;
+      x[j] = v;
+      int f = (mode == 3) ? 0 : (mode == 4 ? (j < 16) : (int)(rnd() & 1));
+      fm |= (uint32_t)f << j;
+    }
+    uint32_t u = 0;
+    const uint32_t want = polar::SubTree<5>::run(x, fm, u);
+    if (polar::BetaTree<5>::run(x, fm) != want) { if (bad < 5) printf("BetaTree it=%d mismatch\n", it); ++bad; }
+    float xc[32];
+    for (int j = 0; j < 32; ++j) xc[j] = fminf(fmaxf(x[j], -30.0f), 30.0f);
+    const uint32_t wc = polar::SubTree<5>::run(xc, fm, u);
+    if (polar::BetaTree<5, true>::run(xc, fm) != wc || polar::BetaTree<5>::run(xc, fm) != wc) {
+      if (bad < 5) printf("BetaTree cl it=%d mismatch\n", it);
+      ++bad;
+    }
+  }
+  return bad;
+}
 int main() {
   int bad = 0;
+  bad += check_beta(40000);
   bad += check<1>(2000); bad += check<2>(4000); bad += check<3>(8000); bad += check<4>(8000); bad += check<5>(20000);
   // transform involution
   for (int i = 0; i < 1000; ++i) { uint32_t v = rnd(); if (polar::ptransform<5>(polar::ptransform<5>(v)) != v) ++bad; }
