@@ -560,3 +560,64 @@ def test_bec_channel_and_link_model():
     m2 = System_BEC_model(cfg, PolarEncoder(fp, n, None), SC_Dec(fp, n), fused=False)
     b2, bh2 = m2(8000, pe)
     assert abs((b2 != bh2).any(-1).float().mean().item() - p_ref) < 8 * np.sqrt(max(p_ref, 1e-3) * (1 - p_ref) / 8000)
+
+
+def test_mc_control_group_follows_the_sequential_stop_rules():
+    """polar_mc_control_group against a plain Python walk of sim.py:79-133 over the same per-iteration counters: items that
+    the sequential loop would not have run at their position (wrong point after an early / late stop, anything behind such an
+    item, anything after the sweep ended, a group planned for another position) must not count."""
+    torch, dk, po, co, dev = _env()
+    rng = np.random.default_rng(5)
+
+    def reference(deltas, points, P, q0_expect, sweep0, state0, tb, tk, mx, early):
+        st, sw = state0.copy(), sweep0.copy()
+        consumed = 0
+        if not sw[1] and sw[2] == q0_expect:
+            for d, p in zip(deltas, points):
+                pc = sw[0]
+                if pc >= P or p != pc:
+                    break
+                st[pc, :4] += d; st[pc, 6] += 1; sw[2] += 1; consumed += 1
+                if tb is not None and st[pc, 0] >= tb: st[pc, 5], st[pc, 4] = 3, 1
+                elif tk is not None and st[pc, 1] >= tk: st[pc, 5], st[pc, 4] = 4, 1
+                elif st[pc, 6] >= mx: st[pc, 5], st[pc, 4] = 1, 1
+                if st[pc, 4]:
+                    if early and st[pc, 1] == 0:
+                        st[pc, 5] = 2; sw[1] = 1
+                        break
+                    sw[0] = pc + 1
+                    if pc + 1 >= P:
+                        sw[1] = 1
+                        break
+        sw[3] += 1; sw[4] = consumed
+        return st, sw
+
+    for trial in range(60):
+        P = int(rng.integers(1, 6)); mx = int(rng.integers(1, 5))
+        tb = None if rng.random() < 0.5 else int(rng.integers(1, 60))
+        tk = None if rng.random() < 0.5 else int(rng.integers(1, 12))
+        early = bool(rng.random() < 0.7)
+        state = torch.zeros((P, 8), dtype=torch.int64, device=dev)
+        sweep = torch.zeros(8, dtype=torch.int64, device=dev)
+        st_ref, sw_ref = np.zeros((P, 8), dtype=np.int64), np.zeros(8, dtype=np.int64)
+        for group in range(6):
+            G = int(rng.integers(1, dk.MC_GROUP_MAX + 1))
+            lo = int(min(sw_ref[0], P - 1))
+            hi = max(min(P, lo + 3) + int(rng.random() < 0.2), lo + 1)
+            pts = np.sort(rng.integers(lo, hi, size=G)).tolist()           # plausible and wrong plans
+            deltas = np.stack([rng.integers(0, 25, G) * (rng.random(G) < 0.8), rng.integers(0, 4, G) * (rng.random(G) < 0.7),
+                               np.full(G, 640), np.full(G, 10)], axis=1).astype(np.int64)
+            expect_q = int(sw_ref[2]) if rng.random() < 0.85 else int(sw_ref[2]) + 1
+            d_dev = torch.from_numpy(deltas).to(dev)
+            dk.mc_control_group(d_dev, pts, state, sweep, expect_q, tb, tk, mx, early)
+            st_ref, sw_ref = reference(deltas, pts, P, expect_q, sw_ref, st_ref, tb, tk, mx, early)
+            assert np.array_equal(state.cpu().numpy(), st_ref), (trial, group)
+            assert np.array_equal(sweep.cpu().numpy(), sw_ref), (trial, group)
+            assert not d_dev.any()                                   # the call clears the counters it consumed or ignored
+    L = dk.lib()
+    st = dk.stream_ptr(dev)
+    import ctypes
+    one = (ctypes.c_int32 * 1)(0)
+    assert L.polar_mc_control_group(None, ctypes.cast(one, ctypes.c_void_p), 1, dk.ptr(state), 1, dk.ptr(sweep), 0, -1, -1, 1, 1, st) == dk.POLAR_EINVAL
+    assert L.polar_mc_control_group(dk.ptr(sweep), ctypes.cast(one, ctypes.c_void_p), 33, dk.ptr(state), 1, dk.ptr(sweep), 0, -1, -1, 1, 1, st) == dk.POLAR_EINVAL
+    assert L.polar_mc_control_group(dk.ptr(sweep), ctypes.cast(one, ctypes.c_void_p), 1, dk.ptr(state), 1, dk.ptr(sweep), 0, -1, -1, 0, 1, st) == dk.POLAR_EINVAL
