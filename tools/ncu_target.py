@@ -16,7 +16,7 @@ what = sys.argv[1] if len(sys.argv) > 1 else "sc"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 dev = torch.device("cuda", 0)
 fz = np.load(os.path.join(ROOT, "tests", "golden", "frozen_sets.npz"))
-if what.startswith("sc") and what != "scl":
+if what.startswith("sc") and not what.startswith("scl"):
     n = {"sc": 1024, "sc2048": 2048, "sc4096": 4096, "sc512": 512}[what]
     k, B = n // 2, (1 << 30) // n
     tables = dk.code_tables(fz["rm_%d_%d" % (n, k)], n, dev)
@@ -24,6 +24,13 @@ if what.startswith("sc") and what != "scl":
     out = torch.empty((B, n // 32), dtype=torch.int32, device=dev)
     for _ in range(reps):
         dk.sc_decode(x, tables, want_info=False, out_packed=out)
+elif what == "scl32":                                       # configs[3]: SCL L=32 n=2048, two waves of the persistent grid
+    n, k, L, B = 2048, 1024, 32, 4736
+    tables = dk.code_tables(fz["rm_2048_1024"], n, dev)
+    _, _, x = dk.awgn_frontend(tables, B, ebnodb2no(2.0, 2, k / n), 4321)
+    out = torch.empty((B, n // 32), dtype=torch.int32, device=dev)
+    for _ in range(reps):
+        dk.scl_decode(x, tables, L, want_info=False, out_packed=out)
 else:
     from my_sn.fec.crc import CRCEncoder
     n, k, L, B = 1024, 512, 8, 1 << 18
