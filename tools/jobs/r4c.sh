@@ -1,4 +1,5 @@
 #!/bin/bash
+# NOTE: the POLAR_SC5_POL experiment switch this script drives was removed again after the measurement (commit "OSD: 16-byte aligned ..."); kept as the record of what DESIGN 4.1 quotes
 python -m pytest tests/test_gpu_osd.py -m gpu -x -q 2>&1 | tail -15
 M=dram__bytes_write.sum,dram__bytes_read.sum,gpu__time_duration.sum
 for pol in 0 2 3 12 13 22 200 100 222 322; do
