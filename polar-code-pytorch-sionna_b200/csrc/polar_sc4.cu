@@ -33,7 +33,7 @@ namespace {
 constexpr unsigned FULLMASK = 0xFFFFFFFFu;
 #define SC4_T(slot)                                                                   \
   do {                                                                                \
-    if (dbg && threadIdx.x == 0 && blockIdx.x == 0) {                                 \
+    if (DBG && threadIdx.x == 0 && blockIdx.x == 0) {                                 \
       const long long t__ = clock64(); g_sc4_dbg[slot] += (unsigned long long)(t__ - tlast); tlast = t__; \
     }                                                                                 \
   } while (0)
@@ -285,9 +285,10 @@ PDEV uint4 bottom128(const float *node, uint64_t fm0, uint64_t fm1) {
   return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)bc, (uint32_t)(bc >> 32));
 }
 
-template <int M, int MODE>
+// DBG: per-phase timeline of warp 0 of CTA 0 (POLAR_SC3_DBG=1) as a separate instantiation: the product kernel carries no timer code
+template <int M, int MODE, bool DBG>
 __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ logit, const uint32_t *__restrict__ fmask_g,
-                                                     int64_t B, int64_t nbatches, int dbg,
+                                                     int64_t B, int64_t nbatches,
                                                      uint32_t *__restrict__ u_packed, float *__restrict__ u_info,
                                                      const int32_t *__restrict__ info_pos, int k) {
   constexpr bool TM = MODE == 1;
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
     for (int idx = N64 - 1; idx >= 1; --idx) nz[idx] = nz[2 * idx] & nz[2 * idx + 1];
   __syncthreads();
 
-  long long tlast = clock64();
+  long long tlast = DBG ? clock64() : 0;
   const long long tstart = tlast;
   const int64_t wstride = (int64_t)gridDim.x * nwarps;
   for (int64_t batch = (int64_t)warp * gridDim.x + blockIdx.x; batch < nbatches; batch += wstride) {
@@ -464,9 +465,9 @@ __global__ void __launch_bounds__(256, 1) sc4_kernel(const float *__restrict__ l
     }
     __syncwarp();
     SC4_T(5);
-    if (dbg && tid == 0 && blockIdx.x == 0) g_sc4_dbg[7] += 1;
+    if (DBG && tid == 0 && blockIdx.x == 0) g_sc4_dbg[7] += 1;
   }
-  if (dbg && tid == 0 && blockIdx.x == 0) g_sc4_dbg[6] += (unsigned long long)(clock64() - tstart);
+  if (DBG && tid == 0 && blockIdx.x == 0) g_sc4_dbg[6] += (unsigned long long)(clock64() - tstart);
   if (TM) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -493,7 +494,7 @@ int launch_sc4_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t 
   while (warps > 1 && sc4_layout(M, TOP, BOT, warps).total > (size_t)max_smem) --warps;
   const Sc4Layout lay = sc4_layout(M, TOP, BOT, warps);
   if (lay.total > (size_t)max_smem) return set_error(POLAR_ENOMEM, "sc: n=%d needs %zu B shared memory per CTA", 1 << M, lay.total);
-  auto kern = sc4_kernel<M, MODE>;
+  auto kern = env_int("POLAR_SC3_DBG", 0) != 0 ? sc4_kernel<M, MODE, true> : sc4_kernel<M, MODE, false>;
   // one persistent CTA per SM.  With tensor memory the CTA takes all 512 columns, so a second CTA must never
   // become resident on the same SM: pad the request above half of the SM's shared memory.
   size_t smem = lay.total;
@@ -504,7 +505,7 @@ int launch_sc4_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t 
   int64_t grid = (nbatches + warps - 1) / warps;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, warps * 32, smem, st>>>(logit, fmask, B, nbatches, env_int("POLAR_SC3_DBG", 0), u_packed, u_info, info_pos, k);
+  kern<<<(unsigned)grid, warps * 32, smem, st>>>(logit, fmask, B, nbatches, u_packed, u_info, info_pos, k);
   count_launch();
   POLAR_CHECK_LAUNCH("sc4_kernel");
   return POLAR_OK;

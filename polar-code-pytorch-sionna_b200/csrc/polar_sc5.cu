@@ -77,7 +77,7 @@ constexpr int kHeaderBytes = 1024;   // + frozen mask words and block flags for 
 
 #define SC5_T(slot)                                                                   \
   do {                                                                                \
-    if (dbg && threadIdx.x == 0 && blockIdx.x == 0) {                                 \
+    if (DBG && threadIdx.x == 0 && blockIdx.x == 0) {                                 \
       const long long t__ = clock64(); g_sc5_dbg[slot] += (unsigned long long)(t__ - tlast); tlast = t__; \
     }                                                                                 \
   } while (0)
@@ -480,9 +480,11 @@ PDEV uint4 bottom128(const float *node, uint64_t fm0, uint64_t fm1) {
   return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)bc, (uint32_t)(bc >> 32));
 }
 
-template <int M, int NS>
+// DBG: the per-phase timeline of warp 0 of CTA 0 (POLAR_SC3_DBG=1); a separate instantiation, so the product kernel carries
+// none of the timer code (the block loop is sensitive to every instruction it does not need)
+template <int M, int NS, bool DBG>
 __global__ void __launch_bounds__(256, 1) sc5_kernel(const float *__restrict__ logit, const uint32_t *__restrict__ fmask_g,
-                                                     int64_t B, int64_t nbatches, int dbg, float *scratch, size_t scratch_per_sm,
+                                                     int64_t B, int64_t nbatches, float *scratch, size_t scratch_per_sm,
                                                      int scr_discard, uint32_t *__restrict__ u_packed, float *__restrict__ u_info,
                                                      const int32_t *__restrict__ info_pos, int k) {
   static_assert(M >= 10 && M <= 13, "sc5: n = 1024 .. 8192");
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(256, 1) sc5_kernel(const float *__restrict__ l
   uint32_t smid;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
   float *scr = scratch + (size_t)smid * (scratch_per_sm / 4) + (size_t)warp * 32 * (N - 512);
-  long long tlast = clock64();
+  long long tlast = DBG ? clock64() : 0;
   const long long tstart = tlast;
   const int64_t wstride = (int64_t)gridDim.x * nwarps;
   for (int64_t batch = (int64_t)warp * gridDim.x + blockIdx.x; batch < nbatches; batch += wstride) {
@@ -678,9 +680,9 @@ __global__ void __launch_bounds__(256, 1) sc5_kernel(const float *__restrict__ l
     }
     __syncwarp();
     SC5_T(5);
-    if (dbg && tid == 0 && blockIdx.x == 0) g_sc5_dbg[7] += 1;
+    if (DBG && tid == 0 && blockIdx.x == 0) g_sc5_dbg[7] += 1;
   }
-  if (dbg && tid == 0 && blockIdx.x == 0) g_sc5_dbg[6] += (unsigned long long)(clock64() - tstart);
+  if (DBG && tid == 0 && blockIdx.x == 0) g_sc5_dbg[6] += (unsigned long long)(clock64() - tstart);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0)
@@ -703,7 +705,8 @@ int launch_sc5_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t 
   float *scratch = sc_scratch();
   if (!scratch)
     return set_error(POLAR_EINVAL, "sc: n=%d needs the per-device stage scratch -- call polar_init(device) once before decoding", N);
-  auto kern = ns == 6 ? sc5_kernel<M, 6> : sc5_kernel<M, 4>;
+  const bool dbg = env_int("POLAR_SC3_DBG", 0) != 0;
+  auto kern = dbg ? (ns == 6 ? sc5_kernel<M, 6, true> : sc5_kernel<M, 4, true>) : (ns == 6 ? sc5_kernel<M, 6, false> : sc5_kernel<M, 4, false>);
   // one persistent CTA per SM: it takes all 512 tensor-memory columns, so a second CTA must never become resident on the
   // same SM: the shared-memory request is padded above half of the SM's
   size_t smem = lay.total;
@@ -714,7 +717,7 @@ int launch_sc5_t(const float *logit, const uint32_t *fmask, int64_t B, uint32_t 
   int64_t grid = (nbatches + warps - 1) / warps;
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, warps * 32, smem, st>>>(logit, fmask, B, nbatches, env_int("POLAR_SC3_DBG", 0), scratch,
+  kern<<<(unsigned)grid, warps * 32, smem, st>>>(logit, fmask, B, nbatches, scratch,
                                               // slots packed back to back: what this launch uses is one dense range (76 MB for
                                               // n = 1024, L2 resident); a sparse 4 MB stride made the L2 write every line back
                                               (size_t)warps * 32 * (N - 512) * 4,
