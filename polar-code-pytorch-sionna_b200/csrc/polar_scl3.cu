@@ -63,6 +63,8 @@ PDEV double fop(double a, double b) {
   return log(1.0 + exp(x + y)) - log(exp(x) + exp(y));
 }
 PDEV double fop(float a, float b) { return fop((double)a, (double)b); }
+PDEV double fop_nc(double a, double b) { return fop(a, b); }
+constexpr bool kEvenLeafInside = false;     // the boxplus of two clipped values stays inside the clip, but only mathematically
 #else
 PDEV float fop(float a, float b) {          // polar_scl.py:93-106 on fp32-representable values: exact
   const float mag = fminf(fminf(fabsf(a), fabsf(b)), 30.0f);
@@ -75,6 +77,14 @@ PDEV double fop(double a, double b) {
   const int hi = (__double2hiint(a) ^ __double2hiint(b)) & 0x80000000;
   return __hiloint2double(__double2hiint(mag) | hi, __double2loint(mag));
 }
+// same for inputs that are outputs of an f themselves (inside [-30, 30]): the clip is the identity
+PDEV double fop_nc(double a, double b) {
+  const double aa = fabs(a), ab = fabs(b);
+  const double mag = (aa < ab) ? aa : ab;
+  const int hi = (__double2hiint(a) ^ __double2hiint(b)) & 0x80000000;
+  return __hiloint2double(__double2hiint(mag) | hi, __double2loint(mag));
+}
+constexpr bool kEvenLeafInside = true;      // an even leaf's LLR is the output of an f: polar_scl.py:81's clip cannot change it
 #endif
 PDEV double gop(double a, double b, unsigned u) {   // polar_scl.py:107-108; u in {0,1}
   const double sa = __hiloint2double(__double2hiint(a) ^ (int)(u << 31), __double2loint(a));
@@ -324,13 +334,14 @@ __global__ void __launch_bounds__(32 * WPC, CPS) scl3_kernel(const Params P) {
       const unsigned fz = (fword >> (i0 & 31)) & 3u;             // bit 0 / 1: leaf i0 / i0+1 frozen
       // ------------------------------------------------------------------ descent to the stage-1 node
       const int t = (i0 == 0) ? M : (__ffs(i0) - 1);             // >= 1
-      double l1a, l1b;
+      double l1a, l1b, x0;                                         // x0: LLR of the even leaf = f(stage 1)
       if (t == 1) {
         // g: stage 2 (slot of the ancestor that wrote it) -> stage 1, beta = the left pair's partial sums
         const double *src = llr_s + 32 * 3 + gbase + (unsigned)((rowL >> 10) & 31u);
         const uint32_t ub = small >> 1;
         l1a = gop(src[0], src[2 * 32], ub & 1u);
         l1b = gop(src[1 * 32], src[3 * 32], (ub >> 1) & 1u);
+        x0 = fop(l1a, l1b);
       } else {
         // every f / g step exists exactly once in the binary: a g (or virtual-pass) switch, then ONE fall-through f
         // cascade down to stage 2.
@@ -364,6 +375,7 @@ __global__ void __launch_bounds__(32 * WPC, CPS) scl3_kernel(const Params P) {
         const double *src = llr_s + 32 * 3 + lane;               // stage 2, own slot
         l1a = fop(src[0], src[2 * 32]);
         l1b = fop(src[1 * 32], src[3 * 32]);
+        x0 = fop_nc(l1a, l1b);                                   // both inputs are outputs of an f: nothing to clip
       }
       {  // stages 1..min(t, TOP) now belong to this path (own slot); stage 0 lives in registers only
         const int top = (t < TOP ? t : TOP);
@@ -372,8 +384,8 @@ __global__ void __launch_bounds__(32 * WPC, CPS) scl3_kernel(const Params P) {
       }
       // info leaf: fork every path, rank the 2L candidates, keep L.  Candidate E = u*L + p (reference slot order
       // [u=0 paths | u=1 paths], polar_scl.py:49-68); two candidates per lane, bitonic sort inside the lane group.
-      auto info_leaf = [&](double x) -> unsigned {
-        const double xc = fmax(fmin(x, kLlrMaxD), -kLlrMaxD);     // polar_scl.py:81
+      auto info_leaf = [&](double x, auto inside) -> unsigned {   // inside: x is the output of an f, i.e. inside the clip already
+        const double xc = (decltype(inside)::value && kEvenLeafInside) ? x : fmax(fmin(x, kLlrMaxD), -kLlrMaxD);     // polar_scl.py:81
         double k0 = pm + sp::softplus_literal(-xc), k1 = pm + sp::softplus_literal(xc);   // u = 0 / u = 1
         int s0 = p, s1 = L + p;
         if constexpr (C::RANK) {
@@ -429,34 +441,35 @@ __global__ void __launch_bounds__(32 * WPC, CPS) scl3_kernel(const Params P) {
         __syncwarp();   // forked paths read their parents' slots from here on
         return (unsigned)(s0 >> LOGL) & 1u;
       };
-      auto frozen_pen = [&](double x) -> double {                // polar_scl.py:82-83 with u = 0
-        return sp::softplus_literal(-fmax(fmin(x, kLlrMaxD), -kLlrMaxD));
+      auto frozen_pen = [&](double x, auto inside) -> double {   // polar_scl.py:82-83 with u = 0
+        return sp::softplus_literal(-((decltype(inside)::value && kEvenLeafInside) ? x : fmax(fmin(x, kLlrMaxD), -kLlrMaxD)));
       };
+      constexpr std::true_type kInside{};                        // the even leaf (f output)
+      constexpr std::false_type kAnywhere{};                     // the odd leaf (g output)
       // ------------------------------------------------------------------ the two leaves
-      const double x0 = fop(l1a, l1b);
       uint32_t cur;                                                // partial sums of the pair: (u0 ^ u1, u1)
       if (fz == 3u) {
-        const double pen0 = frozen_pen(x0), pen1 = frozen_pen(__dadd_rn(l1a, l1b));   // g with u0 = 0
+        const double pen0 = frozen_pen(x0, kInside), pen1 = frozen_pen(__dadd_rn(l1a, l1b), kAnywhere);   // g with u0 = 0
         pm += pen0;
         pm += pen1;
         cur = 0u;
       } else {
         double x1;
         if (fz & 1u) {
-          pm += frozen_pen(x0);
+          pm += frozen_pen(x0, kInside);
           x1 = __dadd_rn(l1a, l1b);
           small &= ~1u;
         } else {
           double *st1 = llr_s + 32 * 1 + lane;                    // stage 1, own slot: the children read it after the fork
           st1[0] = l1a; st1[32] = l1b;
-          const unsigned u0 = info_leaf(x0);
+          const unsigned u0 = info_leaf(x0, kInside);
           small = (small & ~1u) | u0;                              // travels with the path through the next fork
           const double *q1 = llr_s + 32 * 1 + gbase + (unsigned)((rowL >> 5) & 31u);
           x1 = gop(q1[0], q1[32], u0);
         }
         unsigned u1 = 0u;
-        if (fz & 2u) pm += frozen_pen(x1);
-        else u1 = info_leaf(x1);
+        if (fz & 2u) pm += frozen_pen(x1, kAnywhere);
+        else u1 = info_leaf(x1, kAnywhere);
         cur = ((small & 1u) ^ u1) | (u1 << 1);
       }
       // ------------------------------------------------------------------ partial-sum cascade
