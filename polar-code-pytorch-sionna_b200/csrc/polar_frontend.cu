@@ -9,6 +9,8 @@
 // uses counter-based Philox4x32-10, so parity is statistical (BER/BLER inside confidence
 // intervals), never bitwise.  One warp per codeword; 4 positions per lane per step (one Philox call
 // -> two Box-Muller pairs -> one 128-bit store).  HBM-bound on the [B,n] fp32 logit write.
+#include <atomic>
+
 #include "polar_internal.h"
 #include "polar_warp.cuh"
 
@@ -129,9 +131,18 @@ __global__ void __launch_bounds__(256) qpsk_awgn_kernel(uint64_t seed, uint64_t 
 
 using namespace polar;
 
-static unsigned fe_grid(int64_t warps_needed) {
+// Persistent grid-stride kernels: exactly as many CTAs as are resident at once (the kernel needs 40 registers, so 6 CTAs of
+// 256 threads per SM, not 8 -- with 8 x SMs CTAs a third of them ran as a second, mostly empty wave).
+template <class K>
+static unsigned fe_grid(K kern, int64_t warps_needed) {
+  static std::atomic<int> per_sm{0};                     // one value per kernel instantiation (function-local static of a template)
+  int r = per_sm.load(std::memory_order_relaxed);
+  if (r <= 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, kern, 256, 0) != cudaSuccess || r <= 0) { (void)cudaGetLastError(); r = 4; }
+    per_sm.store(r, std::memory_order_relaxed);
+  }
   int64_t g = (warps_needed + 7) / 8;
-  const int64_t cap = (int64_t)device_sm_count() * 8;
+  const int64_t cap = (int64_t)device_sm_count() * r;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (unsigned)g;
@@ -149,11 +160,12 @@ extern "C" int polar_awgn_frontend(uint64_t seed, uint64_t offset, float no, con
   const int m = ilog2(n);
   const float sigma = sqrtf(no * 0.5f);                   // std per real dimension (utils.py:12-13, awgn.py:27)
   const float scale = -2.0f * 1.41421356237309505f / no;  // closed-form demapper
-  const unsigned g = fe_grid(B);
-  if (n <= 1024) frontend_kernel<1><<<g, 256, 0, st>>>(seed, offset, sigma, scale, d_frozen_mask, n, m, B, d_u_packed_out, d_c_packed_out, d_logit_out);
-  else if (n == 2048) frontend_kernel<2><<<g, 256, 0, st>>>(seed, offset, sigma, scale, d_frozen_mask, n, m, B, d_u_packed_out, d_c_packed_out, d_logit_out);
-  else if (n == 4096) frontend_kernel<4><<<g, 256, 0, st>>>(seed, offset, sigma, scale, d_frozen_mask, n, m, B, d_u_packed_out, d_c_packed_out, d_logit_out);
-  else frontend_kernel<8><<<g, 256, 0, st>>>(seed, offset, sigma, scale, d_frozen_mask, n, m, B, d_u_packed_out, d_c_packed_out, d_logit_out);
+#define POLAR_FE_LAUNCH(R) frontend_kernel<R><<<fe_grid(frontend_kernel<R>, B), 256, 0, st>>>(seed, offset, sigma, scale, d_frozen_mask, n, m, B, d_u_packed_out, d_c_packed_out, d_logit_out)
+  if (n <= 1024) POLAR_FE_LAUNCH(1);
+  else if (n == 2048) POLAR_FE_LAUNCH(2);
+  else if (n == 4096) POLAR_FE_LAUNCH(4);
+  else POLAR_FE_LAUNCH(8);
+#undef POLAR_FE_LAUNCH
   count_launch();
   POLAR_CHECK_LAUNCH("frontend");
   return POLAR_OK;
@@ -187,11 +199,12 @@ extern "C" int polar_bec_frontend(uint64_t seed, uint64_t offset, float pe, floa
   if (n >= 4 && ((uintptr_t)d_logit_out & 15)) return set_error(POLAR_EALIGN, "bec frontend: logit_out must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const int m = ilog2(n);
-  const unsigned g = fe_grid(B);
-  if (n <= 1024) frontend_kernel<1, true><<<g, 256, 0, st>>>(seed, offset, pe, llr_max, d_frozen_mask, n, m, B, d_u_packed_out, d_c_packed_out, d_logit_out);
-  else if (n == 2048) frontend_kernel<2, true><<<g, 256, 0, st>>>(seed, offset, pe, llr_max, d_frozen_mask, n, m, B, d_u_packed_out, d_c_packed_out, d_logit_out);
-  else if (n == 4096) frontend_kernel<4, true><<<g, 256, 0, st>>>(seed, offset, pe, llr_max, d_frozen_mask, n, m, B, d_u_packed_out, d_c_packed_out, d_logit_out);
-  else frontend_kernel<8, true><<<g, 256, 0, st>>>(seed, offset, pe, llr_max, d_frozen_mask, n, m, B, d_u_packed_out, d_c_packed_out, d_logit_out);
+#define POLAR_FE_LAUNCH(R) frontend_kernel<R, true><<<fe_grid(frontend_kernel<R, true>, B), 256, 0, st>>>(seed, offset, pe, llr_max, d_frozen_mask, n, m, B, d_u_packed_out, d_c_packed_out, d_logit_out)
+  if (n <= 1024) POLAR_FE_LAUNCH(1);
+  else if (n == 2048) POLAR_FE_LAUNCH(2);
+  else if (n == 4096) POLAR_FE_LAUNCH(4);
+  else POLAR_FE_LAUNCH(8);
+#undef POLAR_FE_LAUNCH
   count_launch();
   POLAR_CHECK_LAUNCH("bec_frontend");
   return POLAR_OK;

@@ -282,7 +282,12 @@ extern "C" int polar_osd_decode(const float *d_logit, const uint32_t *d_gm_rows,
   const OsdLayout lay = osd_layout(n, k);
   if (lay.total > (size_t)device_max_smem_optin()) return set_error(POLAR_ENOMEM, "osd: n=%d k=%d does not fit in shared memory", n, k);
   POLAR_CUDA(cudaFuncSetAttribute(osd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
-  int64_t grid = (int64_t)device_sm_count() * 8;
+  int per_sm = 0;                                        // persistent CTAs: as many as are resident at once
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, osd_kernel, kOsdThreads, lay.total) != cudaSuccess || per_sm <= 0) {
+    (void)cudaGetLastError();
+    per_sm = 4;
+  }
+  int64_t grid = (int64_t)device_sm_count() * per_sm;
   if (grid > B) grid = B;
   osd_kernel<<<(unsigned)grid, kOsdThreads, lay.total, (cudaStream_t)stream>>>(d_logit, d_gm_rows, n, k, t, B, d_c_packed, d_c_f32, d_dist);
   count_launch();

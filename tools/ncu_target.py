@@ -24,6 +24,18 @@ if what.startswith("sc") and not what.startswith("scl"):
     out = torch.empty((B, n // 32), dtype=torch.int32, device=dev)
     for _ in range(reps):
         dk.sc_decode(x, tables, want_info=False, out_packed=out)
+elif what == "fe":                                          # AWGN front end, n = 1024, 2^20 codewords (4 GiB of logits)
+    n, k, B = 1024, 512, 1 << 20
+    tables = dk.code_tables(fz["rm_1024_512"], n, dev)
+    for _ in range(reps):
+        dk.awgn_frontend(tables, B, ebnodb2no(4.0, 2, k / n), 1234)
+elif what == "osd":                                         # OSD n = 128, k = 64, t = 2 (2081 candidates per codeword)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "osd.npz"))
+    n, k, t, B = 128, 64, 2, 1 << 14
+    rows = torch.from_numpy(dk.pack_rows(g["gm_128_64_t1"])).to(dev)
+    x = torch.randn((B, n), device=dev) * 3
+    for _ in range(reps):
+        dk.osd_decode(x, rows, n, k, t)
 elif what == "scl32":                                       # configs[3]: SCL L=32 n=2048, two waves of the persistent grid
     n, k, L, B = 2048, 1024, 32, 4736
     tables = dk.code_tables(fz["rm_2048_1024"], n, dev)
