@@ -94,14 +94,35 @@ __global__ void __launch_bounds__(256) pack_bits_kernel(const float *__restrict_
     if (lane == 0) out[row] = w;
   }
 }
+// [B, nw] packed words -> [B, k] fp32 0./1. at the positions pos[0..k-1] (polar_sc.py:127-133).  One warp per row and
+// pass, a float4 per lane and round (128-bit streaming stores: the 4k bytes per row written are the kernel's only real
+// traffic); VEC = false is the element-wise fallback for k % 4 != 0 or unaligned buffers.
+template <bool VEC>
 __global__ void __launch_bounds__(256) unpack_info_kernel(const uint32_t *__restrict__ packed, const int32_t *__restrict__ pos,
                                                           int nw, int k, int64_t B, float *__restrict__ out) {
-  const int64_t total = B * (int64_t)k;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / k;
-    const int t = (int)(i - b * k);
-    const int p = __ldg(pos + t);
-    out[i] = (float)((__ldg(packed + b * nw + (p >> 5)) >> (p & 31)) & 1u);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t b = warp0; b < B; b += nwarps) {
+    const uint32_t *w = packed + b * nw;
+    float *row = out + b * (int64_t)k;
+    if (VEC) {
+      const int4 *ip = reinterpret_cast<const int4 *>(pos);
+      for (int t4 = lane; t4 < (k >> 2); t4 += 32) {
+        const int4 p = __ldg(ip + t4);
+        float4 o;
+        o.x = (float)((__ldg(w + (p.x >> 5)) >> (p.x & 31)) & 1u);
+        o.y = (float)((__ldg(w + (p.y >> 5)) >> (p.y & 31)) & 1u);
+        o.z = (float)((__ldg(w + (p.z >> 5)) >> (p.z & 31)) & 1u);
+        o.w = (float)((__ldg(w + (p.w >> 5)) >> (p.w & 31)) & 1u);
+        __stcs(reinterpret_cast<float4 *>(row) + t4, o);
+      }
+    } else {
+      for (int t = lane; t < k; t += 32) {
+        const int p = __ldg(pos + t);
+        row[t] = (float)((__ldg(w + (p >> 5)) >> (p & 31)) & 1u);
+      }
+    }
   }
 }
 
@@ -173,7 +194,10 @@ extern "C" int polar_unpack_info_f32(const uint32_t *d_packed, const int32_t *d_
   if (n < 1 || k < 0 || B < 0) return set_error(POLAR_EINVAL, "unpack: bad sizes");
   if (B == 0 || k == 0) return POLAR_OK;
   if (!d_packed || !d_pos || !d_out) return set_error(POLAR_EINVAL, "unpack: null pointer");
-  unpack_info_kernel<<<grid_for(B * (int64_t)k, 256), 256, 0, (cudaStream_t)stream>>>(d_packed, d_pos, POLAR_WORDS(n), k, B, d_out);
+  const bool vec = (k & 3) == 0 && (((uintptr_t)d_pos | (uintptr_t)d_out) & 15) == 0;
+  const unsigned grid = grid_for(B, 8);                    // one warp per row, 8 warps per CTA
+  if (vec) unpack_info_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(d_packed, d_pos, POLAR_WORDS(n), k, B, d_out);
+  else unpack_info_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(d_packed, d_pos, POLAR_WORDS(n), k, B, d_out);
   count_launch();
   POLAR_CHECK_LAUNCH("unpack_info");
   return POLAR_OK;
@@ -186,33 +210,40 @@ extern "C" int polar_unpack_info_f32(const uint32_t *d_packed, const int32_t *d_
 // channel de-interleaver, de-puncturing (logit 0), de-shortening (logit -100), repetition combining (sum) and the
 // sub-block de-interleaver are ONE pass out[b, j] = fill[j] + x[b, src0[j]] + x[b, src1[j]] (negative index = absent).
 namespace polar {
+// one warp per row and pass (no 64-bit division per element; consecutive lanes write consecutive floats of a row)
 __global__ void __launch_bounds__(256) gather_cols_kernel(const float *__restrict__ x, const int32_t *__restrict__ idx, int n_in,
                                                           int n_out, int64_t B, float *__restrict__ out) {
-  const int64_t total = B * (int64_t)n_out;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = t / n_out;
-    const int e = (int)(t - b * n_out);
-    out[t] = __ldg(x + b * n_in + __ldg(idx + e));
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t b = warp0; b < B; b += nwarps) {
+    const float *xr = x + b * (int64_t)n_in;
+    float *o = out + b * (int64_t)n_out;
+    for (int e = lane; e < n_out; e += 32) o[e] = __ldg(xr + __ldg(idx + e));
   }
 }
 __global__ void __launch_bounds__(256) rate_recover_kernel(const float *__restrict__ x, const int32_t *__restrict__ src0,
                                                            const int32_t *__restrict__ src1, const float *__restrict__ fill,
                                                            int n_in, int n_out, int64_t B, float *__restrict__ out) {
-  const int64_t total = B * (int64_t)n_out;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = t / n_out;
-    const int j = (int)(t - b * n_out);
-    const int s0 = __ldg(src0 + j), s1 = __ldg(src1 + j);
-    float v = __ldg(fill + j);
-    if (s0 >= 0) v = __ldg(x + b * n_in + s0);          // received position (fill is 0 there)
-    if (s1 >= 0) v = v + __ldg(x + b * n_in + s1);      // repetition: llr_1 + llr_3 (dec.py:617-620)
-    out[t] = v;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t b = warp0; b < B; b += nwarps) {
+    const float *xr = x + b * (int64_t)n_in;
+    float *o = out + b * (int64_t)n_out;
+    for (int j = lane; j < n_out; j += 32) {
+      const int s0 = __ldg(src0 + j), s1 = __ldg(src1 + j);
+      float v = __ldg(fill + j);
+      if (s0 >= 0) v = __ldg(xr + s0);                    // received position (fill is 0 there)
+      if (s1 >= 0) v = v + __ldg(xr + s1);                // repetition: llr_1 + llr_3 (dec.py:617-620)
+      o[j] = v;
+    }
   }
 }
 }  // namespace polar
 
-static unsigned perm_grid(int64_t total) {
-  int64_t g = (total + 255) / 256;
+static unsigned perm_grid(int64_t rows) {              // one warp per row, 8 warps per CTA
+  int64_t g = (rows + 7) / 8;
   const int64_t cap = (int64_t)polar::device_sm_count() * 16;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
@@ -225,7 +256,7 @@ extern "C" int polar_gather_cols_f32(const float *d_x, const int32_t *d_idx, int
   if (n_in < 1 || n_out < 1 || B < 0) return set_error(POLAR_EINVAL, "gather: bad sizes");
   if (B == 0) return POLAR_OK;
   if (!d_x || !d_idx || !d_out) return set_error(POLAR_EINVAL, "gather: null pointer");
-  gather_cols_kernel<<<perm_grid(B * n_out), 256, 0, (cudaStream_t)stream>>>(d_x, d_idx, n_in, n_out, B, d_out);
+  gather_cols_kernel<<<perm_grid(B), 256, 0, (cudaStream_t)stream>>>(d_x, d_idx, n_in, n_out, B, d_out);
   count_launch();
   POLAR_CHECK_LAUNCH("gather_cols");
   return POLAR_OK;
@@ -237,7 +268,7 @@ extern "C" int polar_rate_recover_f32(const float *d_x, const int32_t *d_src0, c
   if (n_in < 1 || n_out < 1 || B < 0) return set_error(POLAR_EINVAL, "rate_recover: bad sizes");
   if (B == 0) return POLAR_OK;
   if (!d_x || !d_src0 || !d_src1 || !d_fill || !d_out) return set_error(POLAR_EINVAL, "rate_recover: null pointer");
-  rate_recover_kernel<<<perm_grid(B * n_out), 256, 0, (cudaStream_t)stream>>>(d_x, d_src0, d_src1, d_fill, n_in, n_out, B, d_out);
+  rate_recover_kernel<<<perm_grid(B), 256, 0, (cudaStream_t)stream>>>(d_x, d_src0, d_src1, d_fill, n_in, n_out, B, d_out);
   count_launch();
   POLAR_CHECK_LAUNCH("rate_recover");
   return POLAR_OK;
