@@ -69,11 +69,27 @@ __global__ void __launch_bounds__(256) enc_f32_kernel(const float *__restrict__ 
       if (lane == (wd & 31)) x[R == 1 ? 0 : (wd >> 5)] = w;
     }
     warp_polar_transform<R>(x, m, nw);
-    for (int wd = 0; wd < nw; ++wd) {
-      const uint32_t w = __shfl_sync(0xFFFFFFFFu, x[R == 1 ? 0 : (wd >> 5)], wd & 31);
-      const int p = wd * 32 + lane;
-      if (p < n) c[b * (int64_t)n + p] = (float)((w >> lane) & 1u);
-      if (c_packed && lane == 0) c_packed[b * nw + wd] = w;
+    if (c_packed) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (r * 32 + lane < nw) c_packed[b * nw + r * 32 + lane] = x[r];
+    }
+    float *row = c + b * (int64_t)n;
+    if (n >= 128 && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+      // 128 positions per round: lane l writes positions 4l .. 4l+3 of the round as one float4; they sit in word l/8 of it
+      for (int g = 0; g < (n >> 7); ++g) {
+        const int wd = 4 * g + (lane >> 3);
+        const uint32_t w = __shfl_sync(0xFFFFFFFFu, x[R == 1 ? 0 : (wd >> 5)], wd & 31) >> ((4 * lane) & 31);
+        float4 o;
+        o.x = (float)(w & 1u); o.y = (float)((w >> 1) & 1u); o.z = (float)((w >> 2) & 1u); o.w = (float)((w >> 3) & 1u);
+        __stcs(reinterpret_cast<float4 *>(row + 128 * g) + lane, o);
+      }
+    } else {
+      for (int wd = 0; wd < nw; ++wd) {
+        const uint32_t w = __shfl_sync(0xFFFFFFFFu, x[R == 1 ? 0 : (wd >> 5)], wd & 31);
+        const int p = wd * 32 + lane;
+        if (p < n) row[p] = (float)((w >> lane) & 1u);
+      }
     }
   }
 }
