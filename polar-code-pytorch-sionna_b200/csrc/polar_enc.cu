@@ -110,6 +110,21 @@ __global__ void __launch_bounds__(256) pack_bits_kernel(const float *__restrict_
     if (lane == 0) out[row] = w;
   }
 }
+// n a multiple of 128 and 16-byte aligned rows: the tensor is one flat stream of 128-position chunks; a lane loads four
+// positions as one float4, eight lanes assemble a word
+__global__ void __launch_bounds__(256) pack_bits_vec_kernel(const float4 *__restrict__ x, int64_t chunks, uint32_t *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp0; c < chunks; c += nwarps) {
+    const float4 v = __ldcs(x + c * 32 + lane);
+    uint32_t w = ((v.x != 0.0f) | ((v.y != 0.0f) << 1) | ((v.z != 0.0f) << 2) | ((v.w != 0.0f) << 3)) << (4 * (lane & 7));
+    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 1);
+    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 2);
+    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 4);
+    if ((lane & 7) == 0) out[c * 4 + (lane >> 3)] = w;
+  }
+}
 // [B, nw] packed words -> [B, k] fp32 0./1. at the positions pos[0..k-1] (polar_sc.py:127-133).  One warp per row and
 // pass, a float4 per lane and round (128-bit streaming stores: the 4k bytes per row written are the kernel's only real
 // traffic); VEC = false is the element-wise fallback for k % 4 != 0 or unaligned buffers.
@@ -199,7 +214,12 @@ extern "C" int polar_pack_bits_f32(const float *d_x, int n, int64_t B, uint32_t 
   if (B == 0) return POLAR_OK;
   if (!d_x || !d_packed) return set_error(POLAR_EINVAL, "pack: null pointer");
   const int nw = POLAR_WORDS(n);
-  pack_bits_kernel<<<grid_for(B * nw, 8), 256, 0, (cudaStream_t)stream>>>(d_x, n, B, d_packed);
+  if ((n & 127) == 0 && ((uintptr_t)d_x & 15) == 0) {
+    const int64_t chunks = B * (int64_t)(n >> 7);
+    pack_bits_vec_kernel<<<grid_for(chunks, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(d_x), chunks, d_packed);
+  } else {
+    pack_bits_kernel<<<grid_for(B * nw, 8), 256, 0, (cudaStream_t)stream>>>(d_x, n, B, d_packed);
+  }
   count_launch();
   POLAR_CHECK_LAUNCH("pack_bits");
   return POLAR_OK;
