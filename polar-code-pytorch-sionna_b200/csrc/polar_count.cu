@@ -77,9 +77,18 @@ __global__ void __launch_bounds__(256) count_f32_kernel(const float *__restrict_
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   unsigned long long bit_acc = 0, blk_acc = 0;
+  const bool vec = (k & 3) == 0 && (((uintptr_t)a | (uintptr_t)b) & 15) == 0;        // rows of float4: 128-bit loads
   for (int64_t row = warp0; row < B; row += nwarps) {
     unsigned cnt = 0;
-    for (int t = lane; t < k; t += 32) cnt += (__ldg(a + row * k + t) != __ldg(b + row * k + t));
+    if (vec) {
+      const float4 *pa = reinterpret_cast<const float4 *>(a + row * k), *pb = reinterpret_cast<const float4 *>(b + row * k);
+      for (int t = lane; t < (k >> 2); t += 32) {
+        const float4 x = __ldg(pa + t), y = __ldg(pb + t);
+        cnt += (x.x != y.x) + (x.y != y.y) + (x.z != y.z) + (x.w != y.w);
+      }
+    } else {
+      for (int t = lane; t < k; t += 32) cnt += (__ldg(a + row * k + t) != __ldg(b + row * k + t));
+    }
     cnt = warp_sum(cnt);
     bit_acc += cnt; blk_acc += (cnt != 0);
   }
