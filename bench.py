@@ -435,7 +435,7 @@ def main():
         e2e = {"value": world * B / (mod_ms * 1e-3) * k / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": B * n * 4,
                "d2h_bytes_per_step": B * k * 4, "ms_per_step": mod_ms, "codewords_per_s": world * B / (mod_ms * 1e-3),
                "api": "SC_Dec.forward(cpu fp32 tensor [B,n], page-locked) -> cpu fp32 tensor [B,k] (x_run_sn_polar/polar/polar_sc.py; "
-                      "C ABI polar_sc_decode_host_f32: 128 MB chunks, H2D / decode / D2H on two streams)",
+                      "C ABI polar_sc_decode_host_f32: 32 MB chunks (128 MB when the input is pageable and staged), H2D / decode / D2H on two streams)",
                "matches_device_path": ok}
         del out
         # the bit-packed C-ABI side door (round 1's e2e number): 32x less D2H

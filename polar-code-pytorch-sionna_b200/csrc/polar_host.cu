@@ -90,8 +90,13 @@ static void par_memcpy(void *dst, const void *src, size_t bytes) {
   for (auto &t : th) t.join();
 }
 
-static int64_t chunk_codewords(int n, int64_t B) {
-  int64_t c = env_int("POLAR_HOST_CHUNK_MB", 128) * (int64_t)(1 << 20) / ((int64_t)n * 4);
+// Chunk of the H2D / decode / D2H pipeline.  Page-locked input: 32 MB (the first H2D and the last D2H, which nothing
+// overlaps, stay short: 81.7 ms per 4 GiB against 83.4 ms with 128 MB chunks); pageable input goes through the staging
+// memcpy, whose threads want the larger pieces (128 MB: 37.8 ms per GiB against 49 ms with 32 MB).
+static int64_t chunk_codewords(int n, int64_t B, bool staged) {
+  int64_t c = env_int("POLAR_HOST_CHUNK_MB", 0);
+  if (c <= 0) c = staged ? 128 : 32;
+  c = c * (int64_t)(1 << 20) / ((int64_t)n * 4);
   if (c < 1) c = 1;
   if (c > B) c = B;
   return c;
@@ -217,7 +222,7 @@ extern "C" int polar_sc_decode_host_f32(const float *h_logit, const uint32_t *h_
   if ((rc = prepare(C, h_frozen_mask, n, h_u_info_f32 ? h_info_pos : nullptr, k))) return rc;
   POLAR_CUDA(cudaStreamSynchronize(C.st[0]));
   HostJob J{h_logit, h_u_packed, h_u_info_f32, nullptr, n, h_u_info_f32 ? k : 0, 0, B, false, nullptr, 0};
-  return run_chunks(C, J, chunk_codewords(n, B), 0);
+  return run_chunks(C, J, chunk_codewords(n, B, !is_pinned(h_logit)), 0);
 }
 
 extern "C" int polar_sc_decode_host(const float *h_logit, const uint32_t *h_frozen_mask, int n, int64_t B,
@@ -241,7 +246,7 @@ extern "C" int polar_scl_decode_host_f32(const float *h_logit, const uint32_t *h
   if (!guard.ok) return set_error(POLAR_ECUDA, "scl host: cannot select device %d", device);
   int rc = polar_init(device);
   if (rc) return rc;
-  int64_t chunk = chunk_codewords(n, B);
+  int64_t chunk = chunk_codewords(n, B, true);        // the list decoder's time per chunk is not hidden by the copy: large chunks
   if (scl3_supported(n, L) && chunk < B) {
     // the list kernel is persistent: every resident warp decodes the same number of 32/L-codeword groups, so a chunk
     // should be a whole number of such rounds (a 128 MB chunk of n = 1024 is 3.46 rounds: 13 % of the last one idle)

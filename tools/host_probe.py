@@ -14,10 +14,13 @@ n, k, B = 1024, 512, 1 << 18
 fp = fz["rm_1024_512"]
 dec = SC_Dec(fp, n, device=dev)
 x = (torch.randn((B, n)) * 4).float()                      # pageable
+if len(sys.argv) > 1 and sys.argv[1] == "pinned":
+    B = 1 << 20
+    x = (torch.randn((B, n)) * 4).float().pin_memory()
 print("host cores:", os.cpu_count(), "affinity:", len(os.sched_getaffinity(0)))
 ref = None
-for nt in (4, 8, 12, 16):
-    for mb in (32, 64, 128):
+for nt in ((4,) if x.is_pinned() else (4, 8, 12, 16)):
+    for mb in ((16, 32, 64, 128, 256) if x.is_pinned() else (32, 64, 128)):
         dk.set_option("POLAR_HOST_COPY_THREADS", nt); dk.set_option("POLAR_HOST_CHUNK_MB", mb)
         out = dec(x); out = dec(x)
         ts = []
